@@ -1,0 +1,440 @@
+// C-ABI implementation of the hpmvs_b200 engine (see include/hpmvs_b200.h for what each entry point replaces
+// in the reference).  Host side: owns the HBM-resident scene (camera table, RGBX pyramids, covisibility CSR),
+// batch staging buffers and the stream; launches the kernels in patch_kernels.cuh.
+// There is deliberately no CPU implementation behind this ABI.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "patch_kernels.cuh"
+
+#define HP_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t err__ = (call);                                                                     \
+        if (err__ != cudaSuccess) {                                                                     \
+            snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s at %s:%d: %s", #call, __FILE__, __LINE__, \
+                     cudaGetErrorString(err__));                                                        \
+            return HPMVS_E_CUDA;                                                                        \
+        }                                                                                               \
+    } while (0)
+
+static thread_local char g_last_cuda_error[512] = "";
+
+namespace {
+
+struct LevelImage {
+    uchar4* data = nullptr;
+    int w = 0, h = 0, pitch = 0;   // pitch in pixels
+};
+
+inline int pitch_for(int w) { return (w + 3) & ~3; }   // 16-byte aligned rows (TMA-compatible box loads)
+
+// host-side f32 helpers in the same evaluation order as the device ones
+inline float h_dot3(const float* a, const float* b) {
+    const float p0 = a[0] * b[0], p1 = a[1] * b[1], p2 = a[2] * b[2];
+    return p0 + (p1 + p2);
+}
+inline void h_normalized3(const float* a, float* o) {
+    const float z = h_dot3(a, a);
+    if (z > 0.0f) { const float s = sqrtf(z); o[0] = a[0] / s; o[1] = a[1] / s; o[2] = a[2] / s; }
+    else { o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; }
+}
+
+}  // namespace
+
+struct hpmvs_engine {
+    int device = 0;
+    int sm_count = 0;
+    hpmvs_options_t opt{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_kernel_ms = 0.0f;
+    // scene
+    int ncams = 0;
+    std::vector<hp::DevCamera> h_cams;
+    std::vector<std::vector<LevelImage>> images;   // [cam][level]
+    hp::DevCamera* d_cams = nullptr;
+    bool cams_dirty = true;
+    int* d_covis_off = nullptr;
+    int* d_covis_ids = nullptr;
+    bool have_covis = false;
+    // batch staging
+    hpmvs_patch_t* d_in = nullptr;
+    hpmvs_patch_t* d_out = nullptr;
+    float* d_inccs = nullptr;
+    size_t cap_patches = 0, cap_inccs = 0;
+    unsigned char* d_stage = nullptr;
+    size_t cap_stage = 0;
+    int* d_work = nullptr;
+    unsigned long long* d_counters = nullptr;
+    unsigned long long launches = 0;
+    size_t smem_bytes = 0;
+    int blocks_per_sm = 0;
+    std::mutex mu;
+};
+
+static int ensure_patch_capacity(hpmvs_engine* e, size_t n) {
+    if (n <= e->cap_patches) return 0;
+    const size_t cap = n + n / 4 + 1024;
+    if (e->d_in) cudaFree(e->d_in);
+    if (e->d_out) cudaFree(e->d_out);
+    e->d_in = e->d_out = nullptr;
+    e->cap_patches = 0;
+    HP_CUDA(cudaMalloc(&e->d_in, cap * sizeof(hpmvs_patch_t)));
+    HP_CUDA(cudaMalloc(&e->d_out, cap * sizeof(hpmvs_patch_t)));
+    e->cap_patches = cap;
+    return 0;
+}
+
+static int sync_cameras(hpmvs_engine* e) {
+    if (!e->cams_dirty) return 0;
+    for (int c = 0; c < e->ncams; c++)
+        for (int l = 0; l < HPMVS_LEVELS; l++) {
+            const LevelImage& li = e->images[c][l];
+            e->h_cams[c].img[l] = li.data;
+            e->h_cams[c].pitch[l] = li.pitch;
+        }
+    HP_CUDA(cudaMemcpyAsync(e->d_cams, e->h_cams.data(), sizeof(hp::DevCamera) * e->ncams, cudaMemcpyHostToDevice, e->stream));
+    HP_CUDA(cudaStreamSynchronize(e->stream));
+    e->cams_dirty = false;
+    return 0;
+}
+
+static int check_ready(hpmvs_engine* e) {
+    if (!e || e->ncams <= 0 || !e->have_covis) return HPMVS_E_STATE;
+    const int nl = e->opt.maxlevel + 1;
+    for (int c = 0; c < e->ncams; c++)
+        for (int l = 0; l < nl && l < HPMVS_LEVELS; l++)
+            if (!e->images[c][l].data) return HPMVS_E_STATE;
+    return 0;
+}
+
+static hp::KParams make_params(hpmvs_engine* e, const hpmvs_patch_t* d_in, hpmvs_patch_t* d_out, int n) {
+    hp::KParams K{};
+    K.cams = e->d_cams;
+    K.ncams = e->ncams;
+    K.covis_off = e->d_covis_off;
+    K.covis_ids = e->d_covis_ids;
+    K.opt = e->opt;
+    // constants the reference forms with libm on the host (PatchOptimizer.cpp:485,129,239,184,398)
+    K.cos_max_d = cos((double)e->opt.max_angle);
+    K.cos_max_f = cosf(e->opt.max_angle);
+    K.sort_thr = (float)(1.0f - cos(10.0 * M_PI / 180.0));
+    K.angle_scale = (float)(M_PI / 48.0f);
+    K.in = d_in;
+    K.out = d_out;
+    K.n = n;
+    K.work_counter = e->d_work;
+    K.counters = e->d_counters;
+    return K;
+}
+
+extern "C" {
+
+int hpmvs_abi_version(void) { return 1; }
+
+const char* hpmvs_error_string(int code) {
+    switch (code) {
+    case 0: return "ok";
+    case HPMVS_E_ARG: return "invalid argument";
+    case HPMVS_E_CUDA: return g_last_cuda_error[0] ? g_last_cuda_error : "CUDA error";
+    case HPMVS_E_STATE: return "scene incomplete: cameras, all pyramid levels and covisibility must be uploaded first";
+    case HPMVS_E_NODEVICE: return "no CUDA device (this engine has no CPU fallback)";
+    default: return "unknown error";
+    }
+}
+
+int hpmvs_engine_create(const hpmvs_options_t* opt, int device, hpmvs_engine_t** out) {
+    if (!opt || !out) return HPMVS_E_ARG;
+    *out = nullptr;
+    if (opt->maxlevel < 1 || opt->maxlevel >= HPMVS_LEVELS || opt->min_images_per_patch < 1) return HPMVS_E_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return HPMVS_E_NODEVICE;
+    if (device < 0 || device >= ndev) return HPMVS_E_ARG;
+    HP_CUDA(cudaSetDevice(device));
+    hpmvs_engine* e = new hpmvs_engine;
+    e->device = device;
+    e->opt = *opt;
+    cudaDeviceProp prop;
+    HP_CUDA(cudaGetDeviceProperties(&prop, device));
+    e->sm_count = prop.multiProcessorCount;
+    HP_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    HP_CUDA(cudaEventCreate(&e->ev0));
+    HP_CUDA(cudaEventCreate(&e->ev1));
+    HP_CUDA(cudaMalloc(&e->d_work, sizeof(int)));
+    HP_CUDA(cudaMalloc(&e->d_counters, 4 * sizeof(unsigned long long)));
+    HP_CUDA(cudaMemset(e->d_counters, 0, 4 * sizeof(unsigned long long)));
+    e->smem_bytes = sizeof(hp::WarpShared) * hp::WARPS_PER_BLOCK;
+    HP_CUDA(cudaFuncSetAttribute(hp::optimize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    HP_CUDA(cudaFuncSetAttribute(hp::ncc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    HP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->blocks_per_sm, hp::optimize_kernel, hp::WARPS_PER_BLOCK * 32,
+                                                          e->smem_bytes));
+    if (e->blocks_per_sm < 1) e->blocks_per_sm = 1;
+    *out = e;
+    return 0;
+}
+
+void hpmvs_engine_destroy(hpmvs_engine_t* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    for (auto& cam : e->images)
+        for (auto& li : cam)
+            if (li.data) cudaFree(li.data);
+    cudaFree(e->d_cams); cudaFree(e->d_covis_off); cudaFree(e->d_covis_ids);
+    cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_inccs); cudaFree(e->d_stage);
+    cudaFree(e->d_work); cudaFree(e->d_counters);
+    cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
+    cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int hpmvs_engine_set_cameras(hpmvs_engine_t* e, int n, const hpmvs_camera_t* cams) {
+    if (!e || n <= 0 || !cams) return HPMVS_E_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    HP_CUDA(cudaSetDevice(e->device));
+    if (n != e->ncams) {
+        for (auto& cam : e->images)
+            for (auto& li : cam)
+                if (li.data) cudaFree(li.data);
+        e->images.assign(n, std::vector<LevelImage>(HPMVS_LEVELS));
+        if (e->d_cams) cudaFree(e->d_cams);
+        e->d_cams = nullptr;
+        HP_CUDA(cudaMalloc(&e->d_cams, sizeof(hp::DevCamera) * n));
+        e->have_covis = false;
+    }
+    e->ncams = n;
+    e->h_cams.assign(n, hp::DevCamera{});
+    for (int c = 0; c < n; c++) {
+        hp::DevCamera& d = e->h_cams[c];
+        const hpmvs_camera_t& s = cams[c];
+        for (int l = 0; l < HPMVS_LEVELS; l++) {
+            memcpy(d.P[l], s.P[l], sizeof(float) * 12);
+            d.w[l] = s.width[l];
+            d.h[l] = s.height[l];
+        }
+        for (int i = 0; i < 4; i++) d.center[i] = s.center[i];
+        for (int i = 0; i < 3; i++) { d.xaxis[i] = s.xaxis[i]; d.yaxis[i] = s.yaxis[i]; d.zaxis[i] = s.zaxis[i]; }
+        d.xaxis[3] = d.yaxis[3] = d.zaxis[3] = 0.0f;
+        h_normalized3(s.xaxis, d.nx); h_normalized3(s.yaxis, d.ny); h_normalized3(s.zaxis, d.nz);
+        d.nx[3] = d.ny[3] = d.nz[3] = 0.0f;
+        d.ksum = s.k00 + s.k11;
+        d.nlevels = e->opt.maxlevel + 1;
+    }
+    e->cams_dirty = true;
+    return 0;
+}
+
+static int ensure_level(hpmvs_engine* e, int cam, int level, int w, int h) {
+    LevelImage& li = e->images[cam][level];
+    if (li.data && li.w == w && li.h == h) return 0;
+    if (li.data) cudaFree(li.data);
+    li = LevelImage{};
+    const int pitch = pitch_for(w);
+    // two spare rows: bilinear taps of the reference read row ly+1 / column lx+1 (guarded by the 3 px margin)
+    HP_CUDA(cudaMalloc(&li.data, sizeof(uchar4) * (size_t)pitch * (h + 2)));
+    HP_CUDA(cudaMemsetAsync(li.data, 0, sizeof(uchar4) * (size_t)pitch * (h + 2), e->stream));
+    li.w = w; li.h = h; li.pitch = pitch;
+    e->cams_dirty = true;
+    return 0;
+}
+
+int hpmvs_engine_upload_image(hpmvs_engine_t* e, int cam, int level, const uint8_t* rgb, int w, int h, size_t pitch_bytes) {
+    if (!e || !rgb || cam < 0 || cam >= e->ncams || level < 0 || level >= HPMVS_LEVELS || w <= 0 || h <= 0 ||
+        pitch_bytes < (size_t)3 * w)
+        return HPMVS_E_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    HP_CUDA(cudaSetDevice(e->device));
+    int rc = ensure_level(e, cam, level, w, h);
+    if (rc) return rc;
+    const size_t need = (size_t)3 * w * h;
+    if (need > e->cap_stage) {
+        if (e->d_stage) cudaFree(e->d_stage);
+        e->d_stage = nullptr; e->cap_stage = 0;
+        HP_CUDA(cudaMalloc(&e->d_stage, need));
+        e->cap_stage = need;
+    }
+    HP_CUDA(cudaMemcpy2DAsync(e->d_stage, (size_t)3 * w, rgb, pitch_bytes, (size_t)3 * w, h, cudaMemcpyHostToDevice, e->stream));
+    const LevelImage& li = e->images[cam][level];
+    dim3 blk(32, 8), grd((w + 31) / 32, (h + 7) / 8);
+    hp::rgb_to_rgbx_kernel<<<grd, blk, 0, e->stream>>>(e->d_stage, w, h, li.data, li.pitch);
+    e->launches++;
+    HP_CUDA(cudaGetLastError());
+    HP_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->h_cams[cam].w[level] != w || e->h_cams[cam].h[level] != h) return HPMVS_E_ARG;
+    return 0;
+}
+
+int hpmvs_engine_build_pyramid(hpmvs_engine_t* e, int cam) {
+    if (!e || cam < 0 || cam >= e->ncams) return HPMVS_E_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    HP_CUDA(cudaSetDevice(e->device));
+    if (!e->images[cam][0].data) return HPMVS_E_STATE;
+    for (int l = 1; l <= e->opt.maxlevel; l++) {
+        const LevelImage src = e->images[cam][l - 1];
+        const int w2 = src.w / 2, h2 = src.h / 2;
+        if (w2 <= 0 || h2 <= 0) return HPMVS_E_ARG;
+        int rc = ensure_level(e, cam, l, w2, h2);
+        if (rc) return rc;
+        const LevelImage& dst = e->images[cam][l];
+        dim3 blk(32, 8), grd((w2 + 31) / 32, (h2 + 7) / 8);
+        hp::half_xy_kernel<<<grd, blk, 0, e->stream>>>(src.data, src.pitch, src.w, src.h, dst.data, dst.pitch, w2, h2);
+        e->launches++;
+        HP_CUDA(cudaGetLastError());
+        if (e->h_cams[cam].w[l] != w2 || e->h_cams[cam].h[l] != h2) return HPMVS_E_ARG;
+    }
+    HP_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int hpmvs_engine_download_image(hpmvs_engine_t* e, int cam, int level, uint8_t* rgb, size_t pitch_bytes) {
+    if (!e || !rgb || cam < 0 || cam >= e->ncams || level < 0 || level >= HPMVS_LEVELS) return HPMVS_E_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    HP_CUDA(cudaSetDevice(e->device));
+    const LevelImage& li = e->images[cam][level];
+    if (!li.data) return HPMVS_E_STATE;
+    if (pitch_bytes < (size_t)3 * li.w) return HPMVS_E_ARG;
+    const size_t need = (size_t)3 * li.w * li.h;
+    if (need > e->cap_stage) {
+        if (e->d_stage) cudaFree(e->d_stage);
+        e->d_stage = nullptr; e->cap_stage = 0;
+        HP_CUDA(cudaMalloc(&e->d_stage, need));
+        e->cap_stage = need;
+    }
+    dim3 blk(32, 8), grd((li.w + 31) / 32, (li.h + 7) / 8);
+    hp::rgbx_to_rgb_kernel<<<grd, blk, 0, e->stream>>>(li.data, li.pitch, li.w, li.h, e->d_stage);
+    e->launches++;
+    HP_CUDA(cudaGetLastError());
+    HP_CUDA(cudaMemcpy2DAsync(rgb, pitch_bytes, e->d_stage, (size_t)3 * li.w, (size_t)3 * li.w, li.h, cudaMemcpyDeviceToHost, e->stream));
+    HP_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int hpmvs_engine_set_covis(hpmvs_engine_t* e, const int32_t* offsets, const int32_t* ids) {
+    if (!e || !offsets || e->ncams <= 0) return HPMVS_E_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    HP_CUDA(cudaSetDevice(e->device));
+    const int n = e->ncams;
+    const int total = offsets[n];
+    if (total < 0 || (total > 0 && !ids)) return HPMVS_E_ARG;
+    for (int i = 0; i < n; i++) if (offsets[i + 1] < offsets[i]) return HPMVS_E_ARG;
+    for (int i = 0; i < total; i++) if (ids[i] < 0 || ids[i] >= n) return HPMVS_E_ARG;
+    if (e->d_covis_off) cudaFree(e->d_covis_off);
+    if (e->d_covis_ids) cudaFree(e->d_covis_ids);
+    e->d_covis_off = e->d_covis_ids = nullptr;
+    HP_CUDA(cudaMalloc(&e->d_covis_off, sizeof(int) * (n + 1)));
+    HP_CUDA(cudaMalloc(&e->d_covis_ids, sizeof(int) * (total > 0 ? total : 1)));
+    HP_CUDA(cudaMemcpy(e->d_covis_off, offsets, sizeof(int) * (n + 1), cudaMemcpyHostToDevice));
+    if (total > 0) HP_CUDA(cudaMemcpy(e->d_covis_ids, ids, sizeof(int) * total, cudaMemcpyHostToDevice));
+    e->have_covis = true;
+    return 0;
+}
+
+static int launch_optimize(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, hpmvs_patch_t* d_out, cudaStream_t s) {
+    int rc = check_ready(e);
+    if (rc) return rc;
+    rc = sync_cameras(e);
+    if (rc) return rc;
+    HP_CUDA(cudaMemsetAsync(e->d_work, 0, sizeof(int), s));
+    const hp::KParams K = make_params(e, d_in, d_out, n);
+    const int warps = hp::WARPS_PER_BLOCK;
+    int grid = e->sm_count * e->blocks_per_sm;            // persistent: every resident warp slot, a multiple of the SM count
+    const int need = (n + warps - 1) / warps;
+    if (need < grid) grid = need > 0 ? need : 1;
+    HP_CUDA(cudaEventRecord(e->ev0, s));
+    hp::optimize_kernel<<<grid, warps * 32, e->smem_bytes, s>>>(K);
+    HP_CUDA(cudaEventRecord(e->ev1, s));
+    e->launches++;
+    HP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int hpmvs_optimize_batch_device(hpmvs_engine_t* e, int n, const hpmvs_patch_t* d_in, hpmvs_patch_t* d_out, void* stream) {
+    if (!e || n < 0 || (n > 0 && (!d_in || !d_out))) return HPMVS_E_ARG;
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(e->mu);
+    HP_CUDA(cudaSetDevice(e->device));
+    return launch_optimize(e, n, d_in, d_out, stream ? (cudaStream_t)stream : e->stream);
+}
+
+int hpmvs_optimize_batch(hpmvs_engine_t* e, int n, const hpmvs_patch_t* in, hpmvs_patch_t* out, void* stream) {
+    if (!e || n < 0 || (n > 0 && (!in || !out))) return HPMVS_E_ARG;
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(e->mu);
+    HP_CUDA(cudaSetDevice(e->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    int rc = check_ready(e);
+    if (rc) return rc;
+    rc = ensure_patch_capacity(e, (size_t)n);
+    if (rc) return rc;
+    HP_CUDA(cudaMemcpyAsync(e->d_in, in, sizeof(hpmvs_patch_t) * n, cudaMemcpyHostToDevice, s));
+    rc = launch_optimize(e, n, e->d_in, e->d_out, s);
+    if (rc) return rc;
+    HP_CUDA(cudaMemcpyAsync(out, e->d_out, sizeof(hpmvs_patch_t) * n, cudaMemcpyDeviceToHost, s));
+    HP_CUDA(cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&e->last_kernel_ms, e->ev0, e->ev1);
+    return 0;
+}
+
+int hpmvs_ncc_batch(hpmvs_engine_t* e, int n, const hpmvs_patch_t* in, int ref_idx, int robust, float* inccs, void* stream) {
+    if (!e || n < 0 || ref_idx < 0 || ref_idx >= HPMVS_MAX_VIEWS || (n > 0 && (!in || !inccs))) return HPMVS_E_ARG;
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(e->mu);
+    HP_CUDA(cudaSetDevice(e->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    int rc = check_ready(e);
+    if (rc) return rc;
+    rc = sync_cameras(e);
+    if (rc) return rc;
+    rc = ensure_patch_capacity(e, (size_t)n);
+    if (rc) return rc;
+    const size_t ni = (size_t)n * HPMVS_MAX_VIEWS;
+    if (ni > e->cap_inccs) {
+        if (e->d_inccs) cudaFree(e->d_inccs);
+        e->d_inccs = nullptr; e->cap_inccs = 0;
+        HP_CUDA(cudaMalloc(&e->d_inccs, ni * sizeof(float)));
+        e->cap_inccs = ni;
+    }
+    HP_CUDA(cudaMemcpyAsync(e->d_in, in, sizeof(hpmvs_patch_t) * n, cudaMemcpyHostToDevice, s));
+    const hp::KParams K = make_params(e, e->d_in, e->d_out, n);
+    int grid = e->sm_count * e->blocks_per_sm;
+    const int need = (n + hp::WARPS_PER_BLOCK - 1) / hp::WARPS_PER_BLOCK;
+    if (need < grid) grid = need;
+    hp::ncc_kernel<<<grid, hp::WARPS_PER_BLOCK * 32, e->smem_bytes, s>>>(K, ref_idx, robust, e->d_inccs);
+    e->launches++;
+    HP_CUDA(cudaGetLastError());
+    HP_CUDA(cudaMemcpyAsync(inccs, e->d_inccs, ni * sizeof(float), cudaMemcpyDeviceToHost, s));
+    HP_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int hpmvs_engine_counters(hpmvs_engine_t* e, hpmvs_counters_t* out, int reset) {
+    if (!e || !out) return HPMVS_E_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    HP_CUDA(cudaSetDevice(e->device));
+    unsigned long long c[4];
+    HP_CUDA(cudaStreamSynchronize(e->stream));
+    HP_CUDA(cudaMemcpy(c, e->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+    out->patches = c[0]; out->patches_ok = c[1]; out->evals = c[2]; out->textures = c[3];
+    out->kernel_launches = e->launches;
+    if (reset) {
+        HP_CUDA(cudaMemset(e->d_counters, 0, sizeof(c)));
+        e->launches = 0;
+    }
+    return 0;
+}
+
+void* hpmvs_engine_stream(hpmvs_engine_t* e) { return e ? (void*)e->stream : nullptr; }
+
+float hpmvs_engine_last_kernel_ms(hpmvs_engine_t* e) {
+    if (!e) return 0.0f;
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_kernel_ms = ms;
+    return e->last_kernel_ms;
+}
+
+}  // extern "C"

@@ -1,0 +1,831 @@
+// Device code of the hpmvs_b200 engine (sm_100a).  One warp owns one patch at a time and runs the whole of
+// PatchOptimizer::optimize() for it (/root/reference/src/hpmvs/PatchOptimizer.cpp:48-103):
+//   * lane 0 ("leader") executes the scalar control logic: view-list edits and the FP64 BOBYQA state machine
+//     (bobyqa3.h), whose state lives in the warp's shared-memory slab;
+//   * all 32 lanes execute the photometric work co-operatively: per-view projection set-up (lane = view),
+//     7x7 bilinear RGB sampling (lane = sample), and the mean / variance / correlation reductions, which are
+//     evaluated as SEQUENTIAL f32 chains (lane = texture) so that every rounding matches the reference's
+//     scalar loops (Patch2d.hpp:37-84) - that is what makes the BOBYQA trajectory reproducible.
+// Warps pull patches from a global atomic counter (persistent kernel) because the work per patch varies 10x.
+//
+// Compile with -fmad=false: every f32/f64 expression below is written in the reference's evaluation order and
+// must not be contracted into FMAs.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hpmvs_b200.h"
+#include "bobyqa3.h"
+
+namespace hp {
+
+constexpr int MAXV = HPMVS_MAX_VIEWS;
+constexpr int VC = 8;            // texture slots resident per warp (slot 0 = reference view)
+constexpr int TEXN = 147;        // 7*7*3 floats per texture (Patch2d.hpp:31,88)
+constexpr int TEXS = 148;        // padded stride: (148*slot) mod 32 distinct for 8 slots -> conflict-free chains
+constexpr int QS = 52;
+constexpr int WARPS_PER_BLOCK = 4;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct DevCamera {
+    float P[HPMVS_LEVELS][12];
+    float center[4];
+    float xaxis[4], yaxis[4], zaxis[4];   // Camera::xAxis_/yAxis_/zAxis_
+    float nx[4], ny[4], nz[4];            // .normalized() of the above (setOptimizationFields, :388-390)
+    float ksum;                           // kMat_[0](0,0) + kMat_[0](1,1) in f32
+    int nlevels;
+    int w[HPMVS_LEVELS], h[HPMVS_LEVELS];
+    int pitch[HPMVS_LEVELS];              // row pitch in pixels (uchar4)
+    const uchar4* img[HPMVS_LEVELS];
+};
+
+struct KParams {
+    const DevCamera* cams;
+    int ncams;
+    const int* covis_off;
+    const int* covis_ids;
+    hpmvs_options_t opt;
+    double cos_max_d;     // cos((double)MAX_ANGLE): sampleTexture's gate compares float < double (:485)
+    float cos_max_f;      // std::cos(MAX_ANGLE) in f32: addImages / filterImagesByAngle (:129,:239)
+    float sort_thr;       // 1.0f - cos(10 deg) narrowed to f32 (:184)
+    float angle_scale;    // (float)(M_PI / 48.0f) (:398)
+    const hpmvs_patch_t* in;
+    hpmvs_patch_t* out;
+    int n;
+    int* work_counter;
+    unsigned long long* counters;   // patches, ok, evals, textures
+};
+
+struct ViewSetup {
+    float tlx, tly, dxx, dxy, dyx, dyy;
+    int pitch;
+    int pad;
+    const uchar4* img;
+};
+
+struct __align__(16) WarpShared {
+    bq3::State bq;
+    float tex[VC][TEXS];
+    float q[VC][QS];
+    float mean[VC][4];
+    float sigma[VC];
+    int slot_view[VC];
+    float center[4], normal[4];
+    float refCenter[4], refRay[4];
+    float X0[4], Y0[4], Z0[4];
+    float rays[MAXV][4];
+    ViewSetup vs[MAXV];
+    float dots[MAXV];
+    float incc[MAXV];
+    float tmp_f[MAXV];
+    int tmp_i[MAXV];
+    int images[MAXV];
+    int vlist[MAXV];
+    unsigned char vvalid[MAXV];
+    double xcur[3];
+    float scale;
+    int nimg;
+    int textures;
+    int action;
+};
+
+// ----------------------------------------------------------------------------------------------------------
+// f32 helpers in Eigen's evaluation order (see oracle/hpmvs_oracle.cpp header for the conventions)
+// ----------------------------------------------------------------------------------------------------------
+struct f4 { float x, y, z, w; };
+struct f3 { float x, y, z; };
+
+__device__ __forceinline__ f4 ld4(const float* p) { return f4{p[0], p[1], p[2], p[3]}; }
+__device__ __forceinline__ f4 sub4(f4 a, f4 b) { return f4{a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w}; }
+__device__ __forceinline__ f4 add4(f4 a, f4 b) { return f4{a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w}; }
+__device__ __forceinline__ float dot4(f4 a, f4 b) {
+    const float p0 = a.x * b.x, p1 = a.y * b.y, p2 = a.z * b.z, p3 = a.w * b.w;
+    return (p0 + p2) + (p1 + p3);
+}
+__device__ __forceinline__ f4 normalized4(f4 a) {
+    const float z = dot4(a, a);
+    if (z > 0.0f) { const float s = sqrtf(z); return f4{a.x / s, a.y / s, a.z / s, a.w / s}; }
+    return a;
+}
+__device__ __forceinline__ float dot3(f3 a, f3 b) {
+    const float p0 = a.x * b.x, p1 = a.y * b.y, p2 = a.z * b.z;
+    return p0 + (p1 + p2);
+}
+__device__ __forceinline__ f3 normalized3(f3 a) {
+    const float z = dot3(a, a);
+    if (z > 0.0f) { const float s = sqrtf(z); return f3{a.x / s, a.y / s, a.z / s}; }
+    return a;
+}
+__device__ __forceinline__ f3 cross3(f3 a, f3 b) {
+    return f3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+
+// Camera::project (Camera.h:45-62); returns x,y (z is not needed by the path)
+__device__ __forceinline__ void project(const DevCamera& cam, f4 X, int level, float& u, float& v) {
+    const float* p = cam.P[level];
+    float r0 = (p[0] * X.x + p[1] * X.y) + (p[2] * X.z + p[3] * X.w);
+    float r1 = (p[4] * X.x + p[5] * X.y) + (p[6] * X.z + p[7] * X.w);
+    const float r2 = (p[8] * X.x + p[9] * X.y) + (p[10] * X.z + p[11] * X.w);
+    if (r2 <= 0.0f) { u = -65535.0f; v = -65535.0f; return; }
+    r0 = r0 / r2; r1 = r1 / r2;
+    const float lo = -2147483648.0f, hi = 2147483648.0f;   // (float)(INT_MIN + 3.0f), (float)(INT_MAX - 3.0f)
+    u = fmaxf(lo, fminf(hi, r0));
+    v = fmaxf(lo, fminf(hi, r1));
+}
+
+// Camera::getLevel (Camera.cpp:92-95) given fz = |coord - center|
+__device__ __forceinline__ float level_from(const DevCamera& cam, float fz, float scale) {
+    return (float)log2((double)(scale * cam.ksum) / (2.0 * (double)fz));
+}
+__device__ __forceinline__ int leveli_from(const DevCamera& cam, float fz, float scale, int maxLevel) {
+    const int l = (int)roundf(level_from(cam, fz, scale));
+    return max(0, min(maxLevel, l));
+}
+
+// Image::getColor (Image.h:89-115) on the RGBX layout
+__device__ __forceinline__ f3 get_color(const uchar4* img, int pitch, float x, float y) {
+    const int lx = (int)x, ly = (int)y;
+    const float dx1 = x - (float)lx, dx0 = 1.0f - dx1;
+    const float dy1 = y - (float)ly, dy0 = 1.0f - dy1;
+    const float f00 = dx0 * dy0, f01 = dx0 * dy1, f10 = dx1 * dy0, f11 = dx1 * dy1;
+    const uchar4* p = img + (size_t)ly * pitch + lx;
+    const uchar4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + pitch), d = __ldg(p + pitch + 1);
+    f3 o;
+    o.x = ((float)a.x * f00 + (float)c.x * f01) + ((float)b.x * f10 + (float)d.x * f11);
+    o.y = ((float)a.y * f00 + (float)c.y * f01) + ((float)b.y * f10 + (float)d.y * f11);
+    o.z = ((float)a.z * f00 + (float)c.z * f01) + ((float)b.z * f10 + (float)d.z * f11);
+    return o;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// calculatePatchAxis (:532-548): all lanes compute the same registers
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void patch_axes(const DevCamera& rc, f4 n, float scale, f4& xa, f4& ya, f4& za) {
+    f3 z = normalized3(f3{n.x, n.y, n.z});
+    f3 y = normalized3(cross3(z, f3{rc.xaxis[0], rc.xaxis[1], rc.xaxis[2]}));
+    f3 x = normalized3(cross3(y, z));
+    x.x *= scale; x.y *= scale; x.z *= scale;
+    y.x *= scale; y.y *= scale; y.z *= scale;
+    const float s = dot3(normalized3(y), normalized3(f3{rc.yaxis[0], rc.yaxis[1], rc.yaxis[2]}));
+    y.x = y.x * s; y.y = y.y * s; y.z = y.z * s;
+    xa = f4{x.x, x.y, x.z, 0.0f};
+    ya = f4{y.x, y.y, y.z, 0.0f};
+    za = f4{z.x, z.y, z.z, 0.0f};
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// sampleTexture part 1 (:484-507): gate, level, three projections, border test.  lane = view.
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool view_setup(const KParams& K, const DevCamera& cam, f4 c, float scale, f4 xa, f4 ya,
+                                           f4 zgate, ViewSetup& vs) {
+    const f4 d = sub4(ld4(cam.center), c);
+    const float z = dot4(d, d);
+    const float fz = sqrtf(z);                      // == |c - center| as well (same squares)
+    f4 nrm = d;
+    if (z > 0.0f) nrm = f4{d.x / fz, d.y / fz, d.z / fz, d.w / fz};
+    if ((double)dot4(nrm, zgate) < K.cos_max_d) return false;
+    const int lvl = leveli_from(cam, fz, scale, K.opt.maxlevel - 1);
+    float cu, cv, xu, xv, yu, yv;
+    project(cam, c, lvl, cu, cv);
+    project(cam, add4(c, xa), lvl, xu, xv);
+    project(cam, add4(c, ya), lvl, yu, yv);
+    const float dxx = xu - cu, dxy = xv - cv, dyx = yu - cu, dyy = yv - cv;
+    const float hs = 3.5f;
+    const float tlx = cu - hs * dxx - hs * dyx, tly = cv - hs * dxy - hs * dyy;
+    const float trx = cu + hs * dxx - hs * dyx, try_ = cv + hs * dxy - hs * dyy;
+    const float blx = cu - hs * dxx + hs * dyx, bly = cv - hs * dxy + hs * dyy;
+    const float brx = cu + hs * dxx + hs * dyx, bry = cv + hs * dxy + hs * dyy;
+    const float mnx = fminf(fminf(fminf(tlx, trx), blx), brx), mny = fminf(fminf(fminf(tly, try_), bly), bry);
+    const float mxx = fmaxf(fmaxf(fmaxf(tlx, trx), blx), brx), mxy = fmaxf(fmaxf(fmaxf(tly, try_), bly), bry);
+    const int m = 3;
+    if (mnx < (float)m || mny < (float)m || mxx >= (float)(cam.w[lvl] - m) || mxy >= (float)(cam.h[lvl] - m)) return false;
+    vs.tlx = tlx; vs.tly = tly; vs.dxx = dxx; vs.dxy = dxy; vs.dyx = dyx; vs.dyy = dyy;
+    vs.pitch = cam.pitch[lvl];
+    vs.img = cam.img[lvl];
+    return true;
+}
+
+// sampleTexture part 2 (:509-525): 49 samples, lane = sample (two passes); raw RGB goes to tex[slot]
+__device__ __forceinline__ void sample_view(WarpShared& W, int slot, int k, int lane) {
+    const ViewSetup v = W.vs[k];
+    float* t = W.tex[slot];
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {
+        const int s = lane + 32 * pass;
+        if (s < 49) {
+            const int yy = s / 7, xx = s - 7 * yy;
+            float px = v.tlx, py = v.tly;
+            // the reference walks the grid with repeated f32 additions (l += dy; c += dx)
+#pragma unroll
+            for (int i = 0; i < 6; i++) if (i < yy) { px += v.dyx; py += v.dyy; }
+#pragma unroll
+            for (int i = 0; i < 6; i++) if (i < xx) { px += v.dxx; py += v.dxy; }
+            const f3 col = get_color(v.img, v.pitch, px, py);
+            t[3 * s] = col.x; t[3 * s + 1] = col.y; t[3 * s + 2] = col.z;
+        }
+    }
+}
+
+// PatchTex::normalize (Patch2d.hpp:46-84) for slots [first, first+ns): sequential chains, lane = (slot,channel)
+__device__ __forceinline__ void normalize_slots(WarpShared& W, int first, int ns, int lane) {
+    __syncwarp();
+    if (lane < 3 * ns) {
+        const int slot = first + lane / 3, ch = lane % 3;
+        const float* t = W.tex[slot] + ch;
+        float a = 0.0f;
+#pragma unroll 7
+        for (int i = 0; i < 49; i++) a += t[3 * i];
+        W.mean[slot][ch] = a / 49.0f;
+    }
+    __syncwarp();
+    for (int idx = lane; idx < ns * 49; idx += 32) {
+        const int so = idx / 49, s = idx - 49 * so, slot = first + so;
+        const float* t = W.tex[slot] + 3 * s;
+        const float f0 = W.mean[slot][0] - t[0], f1 = W.mean[slot][1] - t[1], f2 = W.mean[slot][2] - t[2];
+        W.q[slot][s] = f0 * f0 + f1 * f1 + f2 * f2;
+    }
+    __syncwarp();
+    if (lane < ns) {
+        const int slot = first + lane;
+        const float* q = W.q[slot];
+        float a = 0.0f;
+#pragma unroll 7
+        for (int i = 0; i < 49; i++) a += q[i];
+        float sg = sqrtf(a / 147.0f);
+        if (sg == 0.0f) sg = 1.0f;
+        W.sigma[slot] = sg;
+    }
+    __syncwarp();
+    for (int idx = lane; idx < ns * TEXN; idx += 32) {
+        const int so = idx / TEXN, i = idx - TEXN * so, slot = first + so;
+        const int ch = i % 3;
+        float v = W.tex[slot][i];
+        v -= W.mean[slot][ch];
+        v /= W.sigma[slot];
+        W.tex[slot][i] = v;
+    }
+    __syncwarp();
+}
+
+// PatchTex::dot (Patch2d.hpp:37-44) of slot 0 with slots [1, 1+no): lane = slot for the 147-term chain
+__device__ __forceinline__ void dot_slots(WarpShared& W, int no, int lane) {
+    for (int idx = lane; idx < no * TEXN; idx += 32) {
+        const int so = idx / TEXN, i = idx - TEXN * so, slot = 1 + so;
+        W.tex[slot][i] = W.tex[0][i] * W.tex[slot][i];
+    }
+    __syncwarp();
+    if (lane < no) {
+        const int slot = 1 + lane;
+        const float* t = W.tex[slot];
+        float a = 0.0f;
+#pragma unroll 7
+        for (int i = 0; i < TEXN; i++) a += t[i];
+        W.dots[W.slot_view[slot]] = a / 147.0f;
+    }
+    __syncwarp();
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// The photometric core shared by objective_fn (:286-311) and setINCCs (:448-474):
+// for the current W.center / W.normal / W.scale and view list, with view `refIdx` as reference, fill
+// W.vvalid[k] (sampleTexture succeeded) and W.dots[k] = refTex.dot(tex_k) for every valid k != refIdx.
+// If the reference view itself fails nothing else is sampled (both callers return early).
+// ----------------------------------------------------------------------------------------------------------
+__device__ __noinline__ void eval_dots(WarpShared& W, const KParams& K, int lane, int refIdx, bool z_is_normal) {
+    const int nimg = W.nimg;
+    const f4 c = ld4(W.center);
+    const f4 n = ld4(W.normal);
+    const float scale = W.scale;
+    f4 xa, ya, za;
+    patch_axes(K.cams[W.images[refIdx]], n, scale, xa, ya, za);
+    const f4 zgate = z_is_normal ? n : za;     // setINCCs passes pNormal_, objective_fn passes pZaxis_ (:456 vs :292)
+    bool ok = false;
+    if (lane < nimg) {
+        ViewSetup vs;
+        ok = view_setup(K, K.cams[W.images[lane]], c, scale, xa, ya, zgate, vs);
+        if (ok) W.vs[lane] = vs;
+        W.vvalid[lane] = ok ? 1 : 0;
+    }
+    const unsigned vmask = __ballot_sync(FULL, ok);
+    __syncwarp();
+    if (!((vmask >> refIdx) & 1u)) return;
+    // ordered list of valid non-reference views
+    const unsigned omask = vmask & ~(1u << refIdx);
+    if (ok && lane != refIdx) W.vlist[__popc(omask & ((1u << lane) - 1u))] = lane;
+    const int nother = __popc(omask);
+    if (lane == 0) W.textures += 1 + nother;
+    __syncwarp();
+    // reference texture -> slot 0, then the others in groups of VC-1
+    int done = 0;
+    bool first = true;
+    do {
+        const int no = min(VC - 1, nother - done);
+        if (first) { sample_view(W, 0, refIdx, lane); }
+        for (int j = 0; j < no; j++) {
+            const int k = W.vlist[done + j];
+            if (lane == 0) W.slot_view[1 + j] = k;
+            sample_view(W, 1 + j, k, lane);
+        }
+        if (first) normalize_slots(W, 0, 1 + no, lane);
+        else normalize_slots(W, 1, no, lane);
+        if (no > 0) dot_slots(W, no, lane);
+        done += no;
+        first = false;
+    } while (done < nother);
+}
+
+// objective_fn's reduction (:294-310), evaluated identically by every lane from shared values
+__device__ __forceinline__ double objective_value(const WarpShared& W, const KParams& K) {
+    if (!W.vvalid[0]) return 2.0;
+    double val = 0.0;
+    int nImgs = 0;
+    for (int ii = 1; ii < W.nimg; ii++) {
+        if (!W.vvalid[ii]) continue;
+        const float r = (float)(1.0 - (double)W.dots[ii]);
+        val += (double)(r / (1.0f + 3.0f * r));
+        nImgs++;
+    }
+    if (nImgs < K.opt.min_images_per_patch - 1) return 2.0;
+    return val / nImgs;
+}
+
+// setINCCs (:448-474): lane = view
+__device__ __forceinline__ void set_inccs(WarpShared& W, const KParams& K, int lane, int refIdx, int robust) {
+    eval_dots(W, K, lane, refIdx, true);
+    if (lane < W.nimg) {
+        float v;
+        if (!W.vvalid[refIdx]) v = 2.0f;
+        else if (lane == refIdx) v = 0.0f;
+        else if (!W.vvalid[lane]) v = 2.0f;
+        else {
+            const float r = 1.0f - W.dots[lane];
+            v = robust ? r / (1.0f + 3.0f * r) : r;
+        }
+        W.incc[lane] = v;
+    }
+    __syncwarp();
+}
+
+// ordered compaction of the view list: keep[lane] for lane < nimg
+__device__ __forceinline__ void compact_images(WarpShared& W, int lane, bool keep) {
+    const int n = W.nimg;
+    const int img = (lane < n) ? W.images[lane] : 0;
+    const unsigned mask = __ballot_sync(FULL, keep && lane < n);
+    __syncwarp();
+    if (keep && lane < n) W.images[__popc(mask & ((1u << lane) - 1u))] = img;
+    if (lane == 0) W.nimg = __popc(mask);
+    __syncwarp();
+}
+
+// filterImagesNCC (:138-152)
+__device__ __forceinline__ bool filter_images_ncc(WarpShared& W, const KParams& K, int lane, float threshold) {
+    set_inccs(W, K, lane, 0, 0);
+    const bool keep = (lane == 0) || (lane < W.nimg && W.incc[lane] < 1.0f - threshold);
+    __syncwarp();
+    compact_images(W, lane, keep);
+    return W.nimg >= K.opt.min_images_per_patch;
+}
+
+// addImages (:225-258).  Returns 1 ok, 0 fail, -1 view list overflow.
+__device__ __forceinline__ int add_images(WarpShared& W, const KParams& K, int lane) {
+    if (W.nimg <= 0) return 0;
+    const int ref = W.images[0];
+    const int n0 = W.nimg;
+    const int beg = K.covis_off[ref], end = K.covis_off[ref + 1];
+    const f4 c = ld4(W.center), nrm = ld4(W.normal);
+    int count = n0;
+    for (int base = beg; base < end; base += 32) {
+        const int j = base + lane;
+        bool keep = false;
+        int cand = 0;
+        if (j < end) {
+            cand = K.covis_ids[j];
+            keep = true;
+            for (int i = 0; i < n0; i++) if (W.images[i] == cand) keep = false;
+            if (keep) {
+                const DevCamera& cam = K.cams[cand];
+                const f4 d = sub4(ld4(cam.center), c);
+                const float z = dot4(d, d);
+                const float fz = sqrtf(z);
+                f4 r = d;
+                if (z > 0.0f) r = f4{d.x / fz, d.y / fz, d.z / fz, d.w / fz};
+                if (dot4(r, nrm) < K.cos_max_f) keep = false;
+                if (keep) {
+                    const int lvl = (int)roundf(level_from(cam, fz, W.scale));
+                    if (lvl < K.opt.minlevel || lvl >= K.opt.maxlevel - 2) keep = false;
+                    if (keep) {
+                        float u, v;
+                        project(cam, c, lvl, u, v);
+                        if (u < 0.0f || (float)(cam.w[lvl] - 1) <= u || v < 0.0f || (float)(cam.h[lvl] - 1) <= v) keep = false;
+                    }
+                }
+            }
+        }
+        const unsigned mask = __ballot_sync(FULL, keep);
+        const int pos = count + __popc(mask & ((1u << lane) - 1u));
+        if (keep && pos < MAXV) W.images[pos] = cand;
+        count += __popc(mask);
+    }
+    __syncwarp();
+    if (count > MAXV) return -1;
+    if (lane == 0) W.nimg = count;
+    __syncwarp();
+    return count >= K.opt.min_images_per_patch ? 1 : 0;
+}
+
+// rays[i] = (cam_i.center - center).normalized() for all views; lane = view
+__device__ __forceinline__ f4 view_ray(const WarpShared& W, const KParams& K, int lane, float* fz_out) {
+    const DevCamera& cam = K.cams[W.images[lane]];
+    const f4 d = sub4(ld4(cam.center), ld4(W.center));
+    const float z = dot4(d, d);
+    const float fz = sqrtf(z);
+    if (fz_out) *fz_out = fz;
+    if (z > 0.0f) return f4{d.x / fz, d.y / fz, d.z / fz, d.w / fz};
+    return d;
+}
+
+// sortImages + getAngleWeightedScales (:183-223, :260-284).  Return value is ignored by the reference (:54).
+__device__ __forceinline__ void sort_images(WarpShared& W, const KParams& K, int lane) {
+    const int nimg = W.nimg;
+    if (nimg == 0) return;
+    float fz0;
+    {
+        const DevCamera& cam0 = K.cams[W.images[0]];
+        const f4 d = sub4(ld4(W.center), ld4(cam0.center));
+        fz0 = sqrtf(dot4(d, d));
+    }
+    const int refLevel = max(0, min(K.opt.maxlevel - 1, (int)roundf(level_from(K.cams[W.images[0]], fz0, W.scale))));
+    bool keep = false;
+    f4 ray = f4{0, 0, 0, 0};
+    float ws = 0.0f;
+    int img = 0;
+    if (lane < nimg) {
+        img = W.images[lane];
+        float fz;
+        ray = view_ray(W, K, lane, &fz);
+        const float cosa = dot4(ray, normalized4(ld4(W.normal)));
+        if (cosa > 0.0f) {
+            keep = true;
+            const DevCamera& cam = K.cams[img];
+            float sc;
+            if (cam.ksum == 0.0f) sc = 1.0f;
+            else sc = (float)(2.0 * (double)fz * (double)(1 << refLevel) / (double)cam.ksum);   // Camera::getScale
+            ws = sc / cosa;
+        }
+    }
+    const unsigned mask = __ballot_sync(FULL, keep);
+    __syncwarp();
+    if (keep) {
+        const int p = __popc(mask & ((1u << lane) - 1u));
+        W.tmp_i[p] = img; W.tmp_f[p] = ws;
+        W.rays[p][0] = ray.x; W.rays[p][1] = ray.y; W.rays[p][2] = ray.z; W.rays[p][3] = ray.w;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int m = __popc(mask);
+        int out = 0;
+        if (m >= 2) {
+            const float thr = K.sort_thr;
+            W.tmp_f[0] = 0.0f;   // keep the reference image
+            while (m > 0) {
+                int index = 0;
+                float best = W.tmp_f[0];
+                for (int j = 1; j < m; j++) if (W.tmp_f[j] < best) { best = W.tmp_f[j]; index = j; }
+                W.images[out++] = W.tmp_i[index];
+                const f4 ri = ld4(W.rays[index]);
+                int jj = 0;
+                for (int j = 0; j < m; j++) {
+                    if (j == index) continue;
+                    const f4 rj = ld4(W.rays[j]);
+                    const float ftmp = fminf(thr, fmaxf(thr / 2.0f, 1.0f - dot4(ri, rj)));
+                    const float wj = W.tmp_f[j] * (thr / ftmp);
+                    W.tmp_i[jj] = W.tmp_i[j];
+                    W.tmp_f[jj] = wj;
+                    W.rays[jj][0] = rj.x; W.rays[jj][1] = rj.y; W.rays[jj][2] = rj.z; W.rays[jj][3] = rj.w;
+                    jj++;
+                }
+                m = jj;
+            }
+        }
+        W.nimg = out;   // pImages_.clear() happens before the size test (:190-193)
+    }
+    __syncwarp();
+}
+
+// assureImageAngles (:105-123)
+__device__ __forceinline__ bool assure_image_angles(WarpShared& W, const KParams& K, int lane) {
+    const int nimg = W.nimg;
+    if (lane < nimg) {
+        const f4 r = view_ray(W, K, lane, nullptr);
+        W.rays[lane][0] = r.x; W.rays[lane][1] = r.y; W.rays[lane][2] = r.z; W.rays[lane][3] = r.w;
+    }
+    __syncwarp();
+    bool found = false;
+    const int npairs = nimg * (nimg - 1) / 2;
+    for (int p = lane; p < npairs; p += 32) {
+        // unrank pair p -> (ii < jj)
+        int ii = 0, rem = p;
+        while (rem >= nimg - 1 - ii) { rem -= nimg - 1 - ii; ii++; }
+        const int jj = ii + 1 + rem;
+        const float a = (float)acos((double)dot4(ld4(W.rays[ii]), ld4(W.rays[jj])));
+        if (a < K.opt.max_angle && a > K.opt.min_angle) found = true;
+    }
+    const bool any = __any_sync(FULL, found);
+    __syncwarp();
+    return any;
+}
+
+// filterImagesByAngle (:125-136)
+__device__ __forceinline__ bool filter_images_by_angle(WarpShared& W, const KParams& K, int lane) {
+    bool keep = false;
+    if (lane < W.nimg) {
+        const f4 r = view_ray(W, K, lane, nullptr);
+        keep = dot4(r, ld4(W.normal)) > K.cos_max_f;
+    }
+    compact_images(W, lane, keep);
+    return W.nimg >= K.opt.min_images_per_patch;
+}
+
+// setRefImage (:154-181)
+__device__ __forceinline__ void set_ref_image(WarpShared& W, const KParams& K, int lane) {
+    const int nimg = W.nimg;
+    if (nimg <= 1) return;
+    int refindex = -1;
+    float refncc = 3.402823466e+38f;
+    for (int ii = 0; ii < nimg; ii++) {
+        set_inccs(W, K, lane, ii, 1);
+        float sum = 0.0f;
+        for (int k = 0; k < nimg; k++) sum = sum + W.incc[k];
+        if (sum < refncc) { refncc = sum; refindex = ii; }
+        __syncwarp();
+    }
+    if (lane == 0 && refindex > 0) {
+        const int t = W.images[0];
+        W.images[0] = W.images[refindex];
+        W.images[refindex] = t;
+    }
+    __syncwarp();
+}
+
+// setCenterNorm (:401-414): leader writes center / normal for parameters x
+__device__ __forceinline__ void set_center_norm(WarpShared& W, const KParams& K, const double* x) {
+    const float x0 = (float)x[0];
+    for (int i = 0; i < 4; i++) W.center[i] = W.refCenter[i] + (x0 * W.refRay[i]) * 1.0f;
+    const float angle1 = (float)(x[1] * (double)K.angle_scale);
+    const float angle2 = (float)(x[2] * (double)K.angle_scale);
+    double s1, c1, s2, c2;
+    sincos((double)angle1, &s1, &c1);
+    sincos((double)angle2, &s2, &c2);
+    const float fx = (float)(s1 * c2);
+    const float fy = (float)s2;
+    const float fz = (float)(-c1 * c2);
+    for (int i = 0; i < 3; i++) W.normal[i] = (W.X0[i] * fx + W.Y0[i] * fy) + W.Z0[i] * fz;
+    W.normal[3] = 0.0f;
+}
+
+// setOptimizationFields + parametersFromCenterNorm (:384-399, :416-446): leader only
+__device__ __forceinline__ void init_parameters(WarpShared& W, const KParams& K, const double* lb, const double* ub, double* x) {
+    const DevCamera& cam = K.cams[W.images[0]];
+    for (int i = 0; i < 3; i++) { W.X0[i] = cam.nx[i]; W.Y0[i] = cam.ny[i]; W.Z0[i] = cam.nz[i]; }
+    for (int i = 0; i < 4; i++) W.refCenter[i] = W.center[i];
+    const f4 rr = normalized4(sub4(ld4(W.refCenter), ld4(cam.center)));
+    W.refRay[0] = rr.x; W.refRay[1] = rr.y; W.refRay[2] = rr.z; W.refRay[3] = rr.w;
+    // c == refCenter here, so x[0] = 0 . refRay / depthScale
+    x[0] = (double)(dot4(sub4(ld4(W.center), ld4(W.refCenter)), rr) / 1.0f);
+    const f3 n3 = f3{W.normal[0], W.normal[1], W.normal[2]};
+    const float fx = dot3(f3{W.X0[0], W.X0[1], W.X0[2]}, n3);
+    const float fy = dot3(f3{W.Y0[0], W.Y0[1], W.Y0[2]}, n3);
+    const float fz = dot3(f3{W.Z0[0], W.Z0[1], W.Z0[2]}, n3);
+    x[2] = (double)(float)asin((double)fy);                       // std::asin(float)
+    const float cosb = (float)cos(fmax(-1.0, fmin(1.0, x[2])));
+    if (cosb == 0.0f) x[1] = 0.0;
+    else {
+        const double sina = (double)(fx / cosb);
+        const double cosa = (double)(-fz / cosb);
+        x[1] = acos(fmin(1.0, fmax(-1.0, cosa)));
+        if (sina < 0.0) x[1] = -x[1];
+    }
+    x[1] /= (double)K.angle_scale;
+    x[2] /= (double)K.angle_scale;
+    for (int i = 0; i < 3; i++) x[i] = fmin(ub[i], fmax(lb[i], x[i]));
+}
+
+// optimizePatch (:322-382)
+__device__ __noinline__ int optimize_patch(WarpShared& W, const KParams& K, int lane, int& nlopt_rc, int& evals, double& score) {
+    nlopt_rc = 0; evals = 0; score = 0.0;
+    if (W.nimg < K.opt.min_images_per_patch) return HPMVS_FAIL_OPT_MINIMAGES;
+    if (lane == 0) {
+        const double lb[3] = {-HUGE_VAL, -23.99999, -23.99999};
+        const double ub[3] = {HUGE_VAL, 23.99999, 23.99999};
+        double x0[3];
+        init_parameters(W, K, lb, ub, x0);
+        W.action = bq3::start(W.bq, x0, lb, ub, 1.e-7, 1000, W.xcur);
+        if (W.action == bq3::ASK) set_center_norm(W, K, W.xcur);
+    }
+    __syncwarp();
+    while (W.action == bq3::ASK) {
+        eval_dots(W, K, lane, 0, false);
+        if (lane == 0) {
+            const double f = objective_value(W, K);
+            W.action = bq3::advance(W.bq, f, W.xcur);
+            if (W.action == bq3::ASK) set_center_norm(W, K, W.xcur);
+        }
+        __syncwarp();
+    }
+    nlopt_rc = W.bq.rc;
+    evals = W.bq.nevals;
+    score = W.bq.minf;
+    const bool success = (nlopt_rc >= 1 && nlopt_rc <= 4);
+    if (!success) {
+        return nlopt_rc == bq3::R_ROUNDOFF_LIMITED ? HPMVS_FAIL_OPT_ROUNDOFF
+               : nlopt_rc == bq3::R_MAXEVAL_REACHED ? HPMVS_FAIL_OPT_MAXEVAL : HPMVS_FAIL_OPT_OTHER;
+    }
+    if (lane == 0) {
+        double xf[3];
+        bq3::result_x(W.bq, xf);
+        set_center_norm(W, K, xf);
+    }
+    __syncwarp();
+    return HPMVS_OK;
+}
+
+// Scene::getColor(const Patch3d&) (Scene.cpp:300-327): lane = view; stable rank by colour norm
+__device__ __forceinline__ f3 patch_color(WarpShared& W, const KParams& K, int lane) {
+    const int nimg = W.nimg;
+    f3 col = f3{0, 0, 0};
+    float nrm = 0.0f;
+    if (lane < nimg) {
+        const DevCamera& cam = K.cams[W.images[lane]];
+        const f4 c = ld4(W.center);
+        const f4 d = sub4(c, ld4(cam.center));
+        const float fz = sqrtf(dot4(d, d));
+        const int lvl = leveli_from(cam, fz, W.scale, cam.nlevels - 1);
+        float u, v;
+        project(cam, c, lvl, u, v);
+        col = get_color(cam.img[lvl], cam.pitch[lvl], u, v);
+        nrm = sqrtf(dot3(col, col));
+        W.tmp_f[lane] = nrm;
+    }
+    __syncwarp();
+    int rank = 0;
+    if (lane < nimg)
+        for (int j = 0; j < nimg; j++) {
+            const float nj = W.tmp_f[j];
+            if (nj < nrm || (nj == nrm && j < lane)) rank++;
+        }
+    const int mid = nimg / 2;
+    const unsigned mmid = __ballot_sync(FULL, lane < nimg && rank == mid);
+    const unsigned mlow = __ballot_sync(FULL, lane < nimg && rank == 0);
+    const int lmid = __ffs(mmid) - 1, llow = __ffs(mlow) - 1;
+    const float nmid = __shfl_sync(FULL, nrm, lmid);
+    const int src = ((double)nmid > 250.0) ? llow : lmid;
+    f3 o;
+    o.x = __shfl_sync(FULL, col.x, src);
+    o.y = __shfl_sync(FULL, col.y, src);
+    o.z = __shfl_sync(FULL, col.z, src);
+    __syncwarp();
+    return o;
+}
+
+__device__ __forceinline__ void load_patch(WarpShared& W, const hpmvs_patch_t& p, int lane) {
+    if (lane < 4) { W.center[lane] = p.center[lane]; W.normal[lane] = p.normal[lane]; }
+    if (lane == 0) { W.scale = p.scale; W.nimg = min(max(p.nimages, 0), MAXV); W.textures = 0; }
+    W.images[lane] = p.images[lane];
+    __syncwarp();
+}
+
+// runOptimization (:48-76); returns the status code
+__device__ __forceinline__ int run_patch(WarpShared& W, const KParams& K, int lane, int& nlopt_rc, int& evals, double& score) {
+    nlopt_rc = 0; evals = 0; score = 0.0;
+    int r = add_images(W, K, lane);
+    if (r < 0) return HPMVS_FAIL_TOO_MANY_VIEWS;
+    if (r == 0) return HPMVS_FAIL_ADD_IMAGES;
+    if (!filter_images_ncc(W, K, lane, K.opt.ncc_alpha_1)) return HPMVS_FAIL_NCC1;
+    sort_images(W, K, lane);
+    if (!assure_image_angles(W, K, lane)) return HPMVS_FAIL_ANGLES;
+    const int st = optimize_patch(W, K, lane, nlopt_rc, evals, score);
+    if (st != HPMVS_OK) return st;
+    r = add_images(W, K, lane);
+    if (r < 0) return HPMVS_FAIL_TOO_MANY_VIEWS;
+    if (r == 0) return HPMVS_FAIL_ADD_IMAGES2;
+    if (!filter_images_ncc(W, K, lane, K.opt.ncc_alpha_2)) return HPMVS_FAIL_NCC2;
+    if (!filter_images_by_angle(W, K, lane)) return HPMVS_FAIL_ANGLE_FILTER;
+    if (!assure_image_angles(W, K, lane)) return HPMVS_FAIL_ANGLES2;
+    set_ref_image(W, K, lane);
+    if (!filter_images_ncc(W, K, lane, K.opt.ncc_alpha_2)) return HPMVS_FAIL_NCC3;
+    return HPMVS_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// K2: the fused optimize kernel.  Persistent warps, dynamic work distribution.
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) optimize_kernel(const KParams K) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpShared& W = reinterpret_cast<WarpShared*>(smem_raw)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    unsigned long long c_ok = 0, c_evals = 0, c_tex = 0, c_n = 0;
+    for (;;) {
+        int pi = 0;
+        if (lane == 0) pi = atomicAdd(K.work_counter, 1);
+        pi = __shfl_sync(FULL, pi, 0);
+        if (pi >= K.n) break;
+        const hpmvs_patch_t& pin = K.in[pi];
+        load_patch(W, pin, lane);
+        int nlopt_rc, evals;
+        double score;
+        const int status = run_patch(W, K, lane, nlopt_rc, evals, score);
+        hpmvs_patch_t& po = K.out[pi];
+        if (status == HPMVS_OK) {
+            const f3 col = patch_color(W, K, lane);
+            if (lane < 4) { po.center[lane] = W.center[lane]; po.normal[lane] = W.normal[lane]; }
+            po.images[lane] = (lane < W.nimg) ? W.images[lane] : 0;
+            if (lane == 0) {
+                po.scale = W.scale; po.nimages = W.nimg;
+                po.color[0] = col.x; po.color[1] = col.y; po.color[2] = col.z;
+                po.ncc = 1.4f;
+            }
+        } else {
+            // rejected: geometry and view list stay as given (PatchOptimizer.cpp:86-93 runs only on success)
+            if (lane < 4) { po.center[lane] = pin.center[lane]; po.normal[lane] = pin.normal[lane]; }
+            po.images[lane] = pin.images[lane];
+            if (lane == 0) {
+                po.scale = pin.scale; po.nimages = pin.nimages;
+                po.color[0] = 0.0f; po.color[1] = 0.0f; po.color[2] = 0.0f;
+                po.ncc = 0.0f;
+            }
+        }
+        if (lane == 0) {
+            po.status = status; po.nlopt_result = nlopt_rc; po.evals = evals; po.textures = W.textures; po.score = score;
+            c_n++; c_ok += (status == HPMVS_OK); c_evals += evals; c_tex += W.textures;
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && c_n) {
+        atomicAdd(&K.counters[0], c_n); atomicAdd(&K.counters[1], c_ok);
+        atomicAdd(&K.counters[2], c_evals); atomicAdd(&K.counters[3], c_tex);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// K1: setINCCs for a batch (parity vehicle for the photometric core)
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) ncc_kernel(const KParams K, int ref_idx, int robust, float* inccs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpShared& W = reinterpret_cast<WarpShared*>(smem_raw)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    unsigned long long c_tex = 0;
+    for (int pi = warp; pi < K.n; pi += nwarps) {
+        load_patch(W, K.in[pi], lane);
+        float v = 2.0f;
+        if (ref_idx < W.nimg) {
+            set_inccs(W, K, lane, ref_idx, robust);
+            if (lane < W.nimg) v = W.incc[lane];
+        }
+        inccs[(size_t)pi * MAXV + lane] = (lane < W.nimg) ? v : 0.0f;
+        if (lane == 0) c_tex += W.textures;
+        __syncwarp();
+    }
+    if (lane == 0 && c_tex) atomicAdd(&K.counters[3], c_tex);
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// image layout kernels
+// ----------------------------------------------------------------------------------------------------------
+// interleaved RGB (tightly packed staging copy) -> pitched RGBX
+__global__ void rgb_to_rgbx_kernel(const unsigned char* __restrict__ src, int w, int h, uchar4* __restrict__ dst, int pitch) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const unsigned char* s = src + 3 * ((size_t)y * w + x);
+    dst[(size_t)y * pitch + x] = make_uchar4(s[0], s[1], s[2], 255);
+}
+__global__ void rgbx_to_rgb_kernel(const uchar4* __restrict__ src, int pitch, int w, int h, unsigned char* __restrict__ dst) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const uchar4 p = src[(size_t)y * pitch + x];
+    unsigned char* d = dst + 3 * ((size_t)y * w + x);
+    d[0] = p.x; d[1] = p.y; d[2] = p.z;
+}
+
+// CImg::get_resize_halfXY (thirdLibs/cimg/CImg.h:21189-21203): 3x3 mask at odd (x,y), Neumann border,
+// f32 left-to-right accumulation, truncation to u8.  One thread per output pixel, all three channels.
+__global__ void half_xy_kernel(const uchar4* __restrict__ src, int sp, int W, int H, uchar4* __restrict__ dst, int dp, int w2, int h2) {
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ox >= w2 || oy >= h2) return;
+    const int x = 2 * ox + 1, y = 2 * oy + 1;
+    const int xp = x - 1, xn = (x + 1 >= W) ? W - 1 : x + 1;
+    const int yp = y - 1, yn = (y + 1 >= H) ? H - 1 : y + 1;
+    const float m0 = 0.07842776544f, m1 = 0.1231940459f, m4 = 0.1935127547f;
+    const uchar4 a0 = src[(size_t)yp * sp + xp], a1 = src[(size_t)yp * sp + x], a2 = src[(size_t)yp * sp + xn];
+    const uchar4 b0 = src[(size_t)y * sp + xp], b1 = src[(size_t)y * sp + x], b2 = src[(size_t)y * sp + xn];
+    const uchar4 c0 = src[(size_t)yn * sp + xp], c1 = src[(size_t)yn * sp + x], c2 = src[(size_t)yn * sp + xn];
+#define HP_TAP(ch) ((float)a0.ch * m0 + (float)a1.ch * m1 + (float)a2.ch * m0 + (float)b0.ch * m1 + (float)b1.ch * m4 + \
+                    (float)b2.ch * m1 + (float)c0.ch * m0 + (float)c1.ch * m1 + (float)c2.ch * m0)
+    const float r = HP_TAP(x), g = HP_TAP(y), b = HP_TAP(z);
+#undef HP_TAP
+    dst[(size_t)oy * dp + ox] = make_uchar4((unsigned char)(int)r, (unsigned char)(int)g, (unsigned char)(int)b, 255);
+}
+
+}  // namespace hp

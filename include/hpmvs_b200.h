@@ -1,0 +1,178 @@
+/* hpmvs_b200 - C ABI of the B200-native patch-optimisation engine.
+ *
+ * This is the drop-in boundary for ONE path of alexlocher/hpmvs: everything below
+ *     bool mo3d::PatchOptimizer::optimize(mo3d::Patch3d&)
+ *         (/root/reference/include/hpmvs/PatchOptimizer.h:39-43, src/hpmvs/PatchOptimizer.cpp:78-103)
+ * i.e. view selection + 3-DoF BOBYQA refinement of the mean robust (1-NCC) photometric score + reference
+ * view re-selection + patch colour, batched over many patches and executed by hand-written sm_100a kernels.
+ * Callers in the reference: Scene::initPatches (src/hpmvs/Scene.cpp:167), CellProcessor::extend / branch
+ * (src/hpmvs/CellProcessor.cpp:129,256).
+ *
+ * Plain C: pointers and sizes only.  All functions return 0 on success or a negative HPMVS_E_* code;
+ * a patch that the reference would reject (optimize() == false) is NOT an error - it is reported per patch
+ * in hpmvs_patch_t.status and its geometry fields are left as given (the reference mutates a Patch3d only
+ * on success, PatchOptimizer.cpp:86-93).  There is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef HPMVS_B200_H
+#define HPMVS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HPMVS_LEVELS 6        /* pyramid levels 0..MAXLEVEL (Image.cpp:38,43; Camera.cpp:36) */
+#define HPMVS_MAX_VIEWS 32    /* capacity of a patch's view list (the reference's std::vector<int> images_) */
+
+/* error codes (function return values) */
+#define HPMVS_E_ARG      (-1)
+#define HPMVS_E_CUDA     (-2)
+#define HPMVS_E_STATE    (-3)   /* cameras / images / covisibility not uploaded yet */
+#define HPMVS_E_NODEVICE (-4)
+
+/* Replaces mo3d::HpmvsOptions (include/hpmvs/HpmvsOptions.h:29-58); only the fields the path reads. */
+typedef struct hpmvs_options {
+    int32_t maxlevel;              /* MAXLEVEL 5 */
+    int32_t minlevel;              /* MINLEVEL 0 */
+    int32_t start_level;           /* START_LEVEL 4 (used by the seeding caller) */
+    float   max_angle;             /* MAX_ANGLE 60 deg in radians, f32 */
+    float   min_angle;             /* MIN_ANGLE 10 deg in radians, f32 */
+    int32_t max_images_per_patch;  /* MAX_IMAGES_PER_PATCH 6 - carried but unused, as in PatchOptimizer.cpp:298 */
+    int32_t min_images_per_patch;  /* MIN_IMAGES_PER_PATCH 3 */
+    float   ncc_alpha_1;           /* NCC_ALPHA_1 0.4 */
+    float   ncc_alpha_2;           /* NCC_ALPHA_2 0.5 */
+} hpmvs_options_t;
+
+/* Replaces the read-only part of mo3d::Camera the path touches (include/hpmvs/Camera.h:87-106):
+ * projection_[level], center_, xAxis_/yAxis_/zAxis_, kMat_[0](0,0),(1,1); plus the pyramid sizes the path
+ * asks mo3d::Image for (Image.h:62-63). */
+typedef struct hpmvs_camera {
+    float   P[HPMVS_LEVELS][3][4];
+    float   center[4];
+    float   xaxis[3], yaxis[3], zaxis[3];
+    float   k00, k11;
+    int32_t width[HPMVS_LEVELS], height[HPMVS_LEVELS];
+} hpmvs_camera_t;
+
+/* per-patch outcome = the stage at which PatchOptimizer::runOptimization (PatchOptimizer.cpp:48-76) bailed out */
+enum {
+    HPMVS_OK = 0,
+    HPMVS_FAIL_ADD_IMAGES = 1,     /* :50  */
+    HPMVS_FAIL_NCC1 = 2,           /* :52  */
+    HPMVS_FAIL_ANGLES = 3,         /* :55  */
+    HPMVS_FAIL_OPT_MINIMAGES = 4,  /* :323 */
+    HPMVS_FAIL_OPT_ROUNDOFF = 5,   /* nlopt::roundoff_limited caught at :369 */
+    HPMVS_FAIL_OPT_MAXEVAL = 6,    /* MAXEVAL_REACHED is not in the success list at :367 */
+    HPMVS_FAIL_OPT_OTHER = 7,
+    HPMVS_FAIL_ADD_IMAGES2 = 8,    /* :63  */
+    HPMVS_FAIL_NCC2 = 9,           /* :65  */
+    HPMVS_FAIL_ANGLE_FILTER = 10,  /* :67  */
+    HPMVS_FAIL_ANGLES2 = 11,       /* :69  */
+    HPMVS_FAIL_NCC3 = 12,          /* :72  */
+    HPMVS_FAIL_TOO_MANY_VIEWS = 13 /* view list would exceed HPMVS_MAX_VIEWS (engine limit, not in the reference) */
+};
+
+/* Replaces the fields of mo3d::Patch3d that optimize() reads and writes (include/hpmvs/Patch3d.h:55-82).
+ * One fixed-size record per patch, 208 bytes, used for input and output. */
+typedef struct hpmvs_patch {
+    /* in / out */
+    float   center[4];             /* center_ (w = 1) */
+    float   normal[4];             /* normal_ (w = 0) */
+    float   scale;                 /* scale_3dx_ */
+    int32_t nimages;               /* images_.size() */
+    int32_t images[HPMVS_MAX_VIEWS]; /* images_, [0] = reference view */
+    /* out */
+    float   color[3];              /* color_ = Scene::getColor(patch), Scene.cpp:300-327 */
+    float   ncc;                   /* ncc_ : the reference hard-codes 1.4 (PatchOptimizer.cpp:95) */
+    int32_t status;                /* HPMVS_OK or HPMVS_FAIL_* */
+    int32_t nlopt_result;          /* nlopt result code of the refinement (1,4 = ok; 5, -4 = rejected) */
+    int32_t evals;                 /* objective evaluations spent by the refinement */
+    int32_t textures;              /* 7x7x3 textures sampled for this patch (unit of the roofline model) */
+    double  score;                 /* final mean robust (1-NCC) of the refinement (discarded by the reference) */
+} hpmvs_patch_t;
+
+typedef struct hpmvs_counters {
+    uint64_t patches;              /* patches processed since creation / last reset */
+    uint64_t patches_ok;
+    uint64_t evals;                /* objective evaluations */
+    uint64_t textures;             /* textures sampled (each = 49 bilinear RGB taps = 588 gathered bytes) */
+    uint64_t kernel_launches;      /* engine kernels launched (all kinds) */
+} hpmvs_counters_t;
+
+typedef struct hpmvs_engine hpmvs_engine_t;
+
+/* Replaces PatchOptimizer::PatchOptimizer(const HpmvsOptions&, const Scene*) (PatchOptimizer.cpp:38-45).
+ * One engine per GPU; `device` is the CUDA ordinal. */
+int  hpmvs_engine_create(const hpmvs_options_t *opt, int device, hpmvs_engine_t **out);
+void hpmvs_engine_destroy(hpmvs_engine_t *e);
+
+/* Replaces the borrowed pointer scene->cameras_.data() (PatchOptimizer.cpp:39). Copies n cameras to HBM. */
+int  hpmvs_engine_set_cameras(hpmvs_engine_t *e, int n, const hpmvs_camera_t *cams);
+
+/* Replaces the borrowed pointer scene->images_.data() (PatchOptimizer.cpp:40): uploads ONE pyramid level of
+ * one view.  `rgb` is host memory, interleaved u8 RGB exactly as mo3d::Image stores it (Image.cpp:62-63),
+ * `pitch_bytes` between rows (>= 3*w).  On the device the level lives as a pitched RGBX u8 array. */
+int  hpmvs_engine_upload_image(hpmvs_engine_t *e, int cam, int level, const uint8_t *rgb, int w, int h,
+                               size_t pitch_bytes);
+
+/* Optional replacement for Image::load's pyramid loop (Image.cpp:56-57, CImg get_resize_halfXY): builds
+ * levels 1..maxlevel of view `cam` on the GPU from the already uploaded level 0 (bit-exact with CImg). */
+int  hpmvs_engine_build_pyramid(hpmvs_engine_t *e, int cam);
+/* Reads a device level back as interleaved RGB (tests, debugging). */
+int  hpmvs_engine_download_image(hpmvs_engine_t *e, int cam, int level, uint8_t *rgb, size_t pitch_bytes);
+
+/* Replaces the borrowed pointer &scene->covis_ (PatchOptimizer.cpp:41): CSR lists, offsets has ncams+1 entries. */
+int  hpmvs_engine_set_covis(hpmvs_engine_t *e, const int32_t *offsets, const int32_t *ids);
+
+/* Replaces n calls of PatchOptimizer::optimize(Patch3d&) (PatchOptimizer.cpp:78-103).
+ * Host buffers (pinned recommended): copies `in` to the device, runs the fused kernel, copies results to `out`
+ * (may alias `in`).  `stream` is a cudaStream_t (NULL = the engine's own stream); the call returns after the
+ * stream has been synchronised. */
+int  hpmvs_optimize_batch(hpmvs_engine_t *e, int n, const hpmvs_patch_t *in, hpmvs_patch_t *out, void *stream);
+
+/* Same work on device-resident records (no copies, asynchronous on `stream`). */
+int  hpmvs_optimize_batch_device(hpmvs_engine_t *e, int n, const hpmvs_patch_t *d_in, hpmvs_patch_t *d_out,
+                                 void *stream);
+
+/* Replaces n calls of PatchOptimizer::setINCCs (PatchOptimizer.cpp:448-474) on patches as given:
+ * inccs[i*HPMVS_MAX_VIEWS + k] = (robust ? r/(1+3r) : r), r = 1-NCC(view ref_idx, view k); 2.0 where invalid. */
+int  hpmvs_ncc_batch(hpmvs_engine_t *e, int n, const hpmvs_patch_t *in, int ref_idx, int robust, float *inccs,
+                     void *stream);
+
+/* ---- host-side scene surface (plain C++ on the host, no GPU needed): what feeds the engine ---- */
+
+/* Replaces mo3d::Camera::init (src/hpmvs/Camera.cpp:34-81) for one NVM camera line
+ * (NVMReader.cpp:63-74: focal f, quaternion wxyz, centre c; principal point = image centre) and fills the
+ * pyramid sizes Image::load would produce (Image.cpp:56-57: each level is floor(w/2) x floor(h/2)). */
+int  hpmvs_camera_from_nvm(double f, const double q_wxyz[4], const double c[3], int width, int height,
+                           int maxlevel, hpmvs_camera_t *out);
+
+/* Replaces Scene::extractCoVisiblilty (src/hpmvs/Scene.cpp:241-298).  Points are given as CSR measurement
+ * lists (meas_offsets[npoints+1], meas_cam[]).  compat != 0 reproduces the reference's counter indexing by
+ * measurement POSITION (Scene.cpp:260-264); compat == 0 counts by camera id.  Two cameras are covisible when
+ * they share >= 50 points.  out_offsets has ncams+1 entries; returns the number of ids written, or the
+ * required capacity (negated) if ids_cap is too small. */
+int  hpmvs_extract_covis(int ncams, int npoints, const int32_t *meas_offsets, const int32_t *meas_cam,
+                         int compat, int32_t *out_offsets, int32_t *out_ids, int ids_cap);
+
+/* Replaces the candidate construction of Scene::initPatches (src/hpmvs/Scene.cpp:116-165), i.e. everything
+ * before the optimize() call: visibility at START_LEVEL with a 2 px margin, normal towards the first view,
+ * scale = getScale(centre, START_LEVEL).  valid[i] = 0 where the reference skips the point. */
+int  hpmvs_seed_patches(const hpmvs_options_t *opt, int ncams, const hpmvs_camera_t *cams, int npoints,
+                        const double *xyz, const int32_t *meas_offsets, const int32_t *meas_cam,
+                        hpmvs_patch_t *out, uint8_t *valid);
+
+int  hpmvs_engine_counters(hpmvs_engine_t *e, hpmvs_counters_t *out, int reset);
+/* The engine's own stream as a cudaStream_t, so callers can record events around asynchronous calls. */
+void *hpmvs_engine_stream(hpmvs_engine_t *e);
+/* Device-side duration of the most recent fused optimize kernel in milliseconds (CUDA events on its stream). */
+float hpmvs_engine_last_kernel_ms(hpmvs_engine_t *e);
+const char *hpmvs_error_string(int code);
+int  hpmvs_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPMVS_B200_H */

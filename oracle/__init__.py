@@ -94,6 +94,7 @@ def lib():
         L.orc_sample_texture.argtypes = [vp, fp, C.c_float, fp, fp, fp, C.c_int, fp]
         L.orc_objective.restype = C.c_double; L.orc_objective.argtypes = [vp, C.c_void_p, dp]
         L.orc_patch_color.argtypes = [vp, C.c_void_p, fp]
+        L.orc_set_cr_asinf.argtypes = [C.c_int]
         L.orc_testfunc_eval.restype = C.c_double; L.orc_testfunc_eval.argtypes = [C.c_int, dp]
         L.orc_bobyqa_testfunc.argtypes = [C.c_int, dp, dp, dp, C.c_double, C.c_int, dp, dp, dp, dp, C.c_int, ip]
         _lib = L
@@ -205,6 +206,11 @@ class OracleScene:
         out = np.zeros(3, np.float32)
         lib().orc_patch_color(self._h, p.ctypes.data, _p(out, C.c_float))
         return out
+
+
+def set_cr_asinf(on: bool) -> None:
+    """See g_cr_asinf in hpmvs_oracle.cpp: libm-independent evaluation of the one asinf on the path."""
+    lib().orc_set_cr_asinf(1 if on else 0)
 
 
 def testfunc(func_id: int, x: Sequence[float]) -> float:

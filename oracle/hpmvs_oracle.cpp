@@ -31,6 +31,12 @@
 
 namespace {
 
+// std::asin(float) at PatchOptimizer.cpp:427 is the only libm call on the path whose result feeds the optimiser
+// directly.  glibc 2.39's asinf is not correctly rounded (differs from RN(asin(x)) for ~3.8% of inputs), newer
+// glibc (CORE-MATH) is.  g_cr_asinf = 1 evaluates it as (float)asin((double)x) = correctly rounded, which is what
+// the GPU engine does; 0 = this box's libm.  Tests run both and state the difference.
+int g_cr_asinf = 0;
+
 // ------------------------------------------------------------------------------------------
 // small fixed-size vector helpers with Eigen's evaluation order
 // ------------------------------------------------------------------------------------------
@@ -489,7 +495,7 @@ struct PatchOptimizer {
         const float fx = dot3(imgX[0], n3);
         const float fy = dot3(imgY[0], n3);
         const float fz = dot3(imgZ[0], n3);
-        x[2] = std::asin(fy);
+        x[2] = g_cr_asinf ? (double)(float)std::asin((double)fy) : (double)std::asin(fy);
         const float cosb = std::cos(std::max(-1.0, std::min(1.0, x[2])));
         if (cosb == 0.0) x[1] = 0.0;
         else {
@@ -870,6 +876,8 @@ void orc_patch_color(void* scene, const orc_patch_t* patch, float rgb[3]) {
     const V3 col = patch_color(*static_cast<Scene*>(scene), c, patch->scale, patch->images, patch->nimages);
     rgb[0] = col[0]; rgb[1] = col[1]; rgb[2] = col[2];
 }
+
+void orc_set_cr_asinf(int on) { g_cr_asinf = on; }
 
 double orc_testfunc_eval(int func_id, const double x[3]) { return testfunc(func_id, x); }
 

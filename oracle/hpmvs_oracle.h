@@ -103,6 +103,9 @@ double orc_objective(void *scene, const orc_patch_t *patch, const double x[3]);
 /* Scene::getColor(const Patch3d&) (Scene.cpp:300-327) */
 void  orc_patch_color(void *scene, const orc_patch_t *patch, float rgb[3]);
 
+/* 1: evaluate std::asin(float) of PatchOptimizer.cpp:427 correctly rounded instead of with this box's libm */
+void  orc_set_cr_asinf(int on);
+
 /* Real nlopt BOBYQA (n=3, default initial step, xtol_rel, maxeval) on a built-in analytic test
  * function; records every evaluated point.  Used to pin the product's own BOBYQA. */
 int   orc_bobyqa_testfunc(int func_id, const double x0[3], const double lb[3], const double ub[3],
