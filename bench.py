@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py - optimized patches/sec of the PatchOptimizer::optimize() hot path on synthetic N-view scenes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload plane8|city100]
+
+One "step" = one pass of the hot path over one batch of seed patches (BASELINE.json configs[1]:
+8-view synthetic planar scene, 10k seed patches).  Prints ONE JSON line (rank 0).
+
+* value        : optimized (status OK) patches / s, whole job, patch records already resident in HBM,
+                 timed with CUDA events on the launching stream (the engine's fused kernel only).
+* e2e          : same metric through the public C ABI call hpmvs_optimize_batch() with PINNED HOST buffers:
+                 H2D of the batch + kernel + D2H of the results inside the timed region.
+* roofline     : algorithmic gather bytes (588 B per sampled 7x7x3 texture + 2*208 B record I/O per patch,
+                 SURVEY section 8d) / kernel time, against the measured HBM peak in MEASURED_PEAKS.json.
+* cpu_baseline : the oracle (CPU restatement + the reference's real BOBYQA) on this box's host cores, bounded sample.
+--impl reference times that CPU path alone with all host threads (the reference itself is CPU-only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TEX_BYTES = 588          # 49 samples x 4 taps x 3 channels x 1 B  (PatchOptimizer.cpp:512-524, Image.h:104-113)
+REC_BYTES = 208          # sizeof(hpmvs_patch_t)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="plane8", choices=["plane8", "city100", "tiny"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="patches in the cpu_baseline sample (0 = auto)")
+    return ap.parse_args()
+
+
+def workload_scene(name: str, rank: int = 0):
+    """Synthetic scene + seed points for a workload; every rank gets the same images, its own seed points."""
+    from hpmvs_b200 import synth
+    if name == "plane8":
+        return synth.plane_scene(n_views=8, width=1280, height=960, focal=1200.0, radius=8.0, arc_deg=40.0,
+                                 n_seeds=10000, extent=2.5, seed=2 + 1000 * rank, tex_size=1024), \
+            "8-view 1280x960 synthetic plane, 10k seed patches (BASELINE.json configs[1])"
+    if name == "tiny":
+        return synth.plane_scene(n_views=8, width=640, height=480, focal=600.0, n_seeds=2000, seed=2 + 1000 * rank,
+                                 tex_size=512), "8-view 640x480 synthetic plane, 2k seed patches (smoke size)"
+    return synth.city_scene(n_views=100, width=1920, height=1080, n_seeds=100000, seed=4 + 1000 * rank), \
+        "100-view 1080p synthetic city block, 100k seed patches (BASELINE.json configs[3] on 1 GPU)"
+
+
+def cached_scene(name: str, rank: int):
+    """Scenes are deterministic; cache the rendered one under /tmp so repeated runs on one box skip the ray caster."""
+    import pickle
+    path = f"/tmp/hpmvs_b200_scene_{name}_{rank}.pkl"
+    if os.path.exists(path):
+        try:
+            with open(path, "rb") as fh:
+                return pickle.load(fh)
+        except Exception:
+            pass
+    sc = workload_scene(name, rank)
+    try:
+        with open(path + ".tmp", "wb") as fh:
+            pickle.dump(sc, fh, protocol=4)
+        os.replace(path + ".tmp", path)
+    except Exception:
+        pass
+    return sc
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons with nvidia-smi while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.samples.append(line.strip())
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        time.sleep(0.15)
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_rate(scene, seeds_or, sample: int, threads: int, repeats: int = 1):
+    """Oracle on host cores: optimized patches/s on the first `sample` seeds (bounded CPU work)."""
+    import oracle
+    orc = oracle.OracleScene.from_synth(scene)
+    batch = seeds_or[:sample]
+    best = None
+    ok = 0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        out = orc.optimize_batch(batch, nthreads=threads)
+        dt = time.perf_counter() - t0
+        ok = int((out["status"] == 0).sum())
+        best = dt if best is None else min(best, dt)
+    return ok / best, best, ok, len(batch)
+
+
+def to_oracle(p_en):
+    import oracle
+    out = np.zeros(len(p_en), oracle.PATCH_DTYPE)
+    for f in ("center", "normal", "scale", "nimages"):
+        out[f] = p_en[f]
+    out["images"][:, :p_en["images"].shape[1]] = p_en["images"]
+    return out
+
+
+def run_reference(args):
+    """--impl reference: the CPU path (oracle port + the reference's real BOBYQA) with all host threads."""
+    import oracle
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scene, desc = cached_scene(args.workload, 0)
+    orc = oracle.OracleScene.from_synth(scene)
+    seeds, valid = orc.seed_patches(scene.points, scene.meas_offsets, scene.meas_cam)
+    seeds = seeds[valid]
+    threads = host_threads()
+    # each step = a bounded sample of the workload: ~2 s of wall time per step at ~1.7k patches/s/thread
+    sample = args.cpu_sample or int(min(len(seeds), max(256, 3000 * threads // 8)))
+    batch = seeds[:sample]
+    for _ in range(args.warmup):
+        orc.optimize_batch(batch[: max(64, sample // 8)], nthreads=threads)
+    t_tot, ok_tot = 0.0, 0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        out = orc.optimize_batch(batch, nthreads=threads)
+        t_tot += time.perf_counter() - t0
+        ok_tot += int((out["status"] == 0).sum())
+    val = ok_tot / t_tot
+    line = {"impl": "reference", "metric": "optimized patches/sec", "value": val, "unit": "patches/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 samples / f64 optimizer", "data": "synthetic",
+            "config": {"workload": desc, "patches_per_step": int(sample)},
+            "cpu_baseline": {"value": val, "unit": "patches/s", "cores": threads, "kind": "port",
+                             "sample": f"first {sample} of {len(seeds)} seed patches per step, oracle restatement of PatchOptimizer "
+                                       f"+ the reference's real nlopt BOBYQA, OpenMP over patches as Scene.cpp:114"},
+            "e2e": {"value": val, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import hpmvs_b200 as hp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: hpmvs_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- scene (weak scaling: same views on every GPU, a different 10k-seed shard per rank) -----------------
+    scene, desc = cached_scene(args.workload, rank)
+    opts = hp.Options.defaults()
+    eng = hp.Engine.from_synth(scene, opts, device=local_rank)
+    seeds, valid = hp.seed_patches(opts, eng.cameras, scene.points, scene.meas_offsets, scene.meas_cam)
+    seeds = np.ascontiguousarray(seeds[valid])
+    n = len(seeds)
+
+    stream = torch.cuda.Stream()          # a real (non-legacy) stream: its handle is what the C ABI launches on
+    torch.cuda.set_stream(stream)
+    sptr = stream.cuda_stream
+    assert sptr != 0
+    rec = torch.from_numpy(seeds.view(np.uint8).reshape(n, REC_BYTES))
+    h_in = torch.empty((n, REC_BYTES), dtype=torch.uint8).pin_memory()
+    h_in.copy_(rec)
+    h_out = torch.empty((n, REC_BYTES), dtype=torch.uint8).pin_memory()
+    d_in = h_in.to("cuda", non_blocking=False)
+    d_out = torch.empty_like(d_in)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        eng.optimize_device(n, d_in.data_ptr(), d_out.data_ptr(), sptr)
+
+    def step_e2e():
+        eng.optimize_ptr(n, h_in.data_ptr(), h_out.data_ptr(), sptr)
+
+    # ---- warm-up ---------------------------------------------------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    torch.cuda.synchronize()
+    eng.counters(reset=True)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+
+    # ---- timed: K steps, kernel only, records resident in HBM, L2 flushed between steps ---------------------
+    barrier()
+    evs = []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step_device()
+        e1.record(stream)
+        evs.append((e0, e1))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    kernel_ms = [a.elapsed_time(b) for a, b in evs]
+    t_dev = sum(kernel_ms) / 1e3
+    cnt = eng.counters(reset=True)
+    ok_per_step = cnt.patches_ok / args.steps
+    tex_per_step = cnt.textures / args.steps
+    evals_per_step = cnt.evals / args.steps
+    launches_timed = int(cnt.kernel_launches)
+
+    # ---- timed: e2e through the C ABI with pinned host buffers ----------------------------------------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        step_e2e()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    # subtract nothing: the flush is a few hundred microseconds per step and stays inside (conservative)
+    clocks = sampler.finish() if sampler else None
+    out_np = h_out.numpy().view(hp.PATCH_DTYPE).reshape(n)
+    ok_e2e = int((out_np["status"] == 0).sum())
+
+    # ---- reduce over ranks -------------------------------------------------------------------------------------
+    stats = torch.tensor([t_dev, t_e2e, ok_per_step, tex_per_step, float(n), evals_per_step, float(ok_e2e)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        t_dev_max, t_e2e_max = float(mx[0]), float(mx[1])
+        ok_all, tex_all, n_all, evals_all, ok_e2e_all = float(sm[2]), float(sm[3]), float(sm[4]), float(sm[5]), float(sm[6])
+    else:
+        t_dev_max, t_e2e_max = t_dev, t_e2e
+        ok_all, tex_all, n_all, evals_all, ok_e2e_all = ok_per_step, tex_per_step, float(n), evals_per_step, float(ok_e2e)
+
+    if rank == 0:
+        value = ok_all * args.steps / t_dev_max
+        e2e_val = ok_e2e_all * args.steps / t_e2e_max
+        # roofline of the dominant (only) kernel on THIS rank: algorithmic bytes per launch / mean launch time
+        alg_bytes = TEX_BYTES * tex_per_step + 2 * REC_BYTES * n
+        mean_launch_s = t_dev / args.steps
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
+        achieved = alg_bytes / mean_launch_s / 1e9
+        # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
+        cpu = None
+        if world == 1:
+            import oracle
+            threads = host_threads()
+            sample = args.cpu_sample or int(min(n, max(512, 4000 * threads // 8)))
+            rate, dt, okc, ns = cpu_reference_rate(scene, to_oracle(seeds), sample, threads)
+            cpu = {"value": rate, "unit": "patches/s", "cores": threads, "kind": "port",
+                   "sample": f"first {ns} of {n} seed patches of the same batch, {okc} optimized, {dt:.2f} s wall; oracle restatement of "
+                             f"PatchOptimizer + the reference's real nlopt BOBYQA (HPMVS itself cannot be built here), OpenMP over patches"}
+        line = {"metric": "optimized patches/sec", "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": 1e3 * t_dev_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 samples / f64 optimizer", "data": "synthetic",
+                "config": {"workload": desc, "patches_per_step_per_gpu": int(n), "optimized_per_step": ok_all,
+                           "evals_per_step": evals_all, "textures_per_step": tex_all, "l2": "flushed between steps (256 MiB write)",
+                           "parallelism": f"patch shards x{world}, scene replicated, no data-path collective",
+                           "wall_s_timed_region": t_wall},
+                "clocks": clocks,
+                "e2e": {"value": e2e_val, "unit": "patches/s", "h2d_bytes_per_step": int(n * REC_BYTES), "d2h_bytes_per_step": int(n * REC_BYTES),
+                        "ms_per_step": 1e3 * t_e2e_max / args.steps},
+                "gpu_launches": launches_timed,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": peak_src, "kernel": "hp::optimize_kernel",
+                             "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": 1e3 * mean_launch_s,
+                             "note": "algorithmic gather bytes (588 B/texture, no reuse credit); the footprint is L1-resident so DRAM traffic is far lower - kernel is issue/latency bound, see DESIGN.md"},
+                "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

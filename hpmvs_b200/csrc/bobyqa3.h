@@ -26,11 +26,20 @@
 
 #include <math.h>
 
+// The loops below have tiny constant trip counts (3, 7, 10).  Fully unrolled, the state machine grows to >300 KB of
+// SASS and the kernel becomes instruction-fetch bound (ncu: 65% "no_instructions" stalls); kept rolled it fits the
+// SM's instruction cache.
+#if defined(__CUDA_ARCH__)
+#define BQ_NOUNROLL _Pragma("unroll 1")
+#else
+#define BQ_NOUNROLL
+#endif
+
 namespace bq3 {
 
 enum : int { N = 3, NPT = 7, NDIM = 10, NPTM = 3, NP = 4, NH = 6 };
 
-// nlopt_result values the reference tests for (api/nlopt.h:160-170)
+// nlopt_result values the reference tests BQ_NOUNROLL for (api/nlopt.h:160-170)
 enum Result : int {
     R_FAILURE = -1, R_INVALID_ARGS = -2, R_ROUNDOFF_LIMITED = -4,
     R_SUCCESS = 1, R_XTOL_REACHED = 4, R_MAXEVAL_REACHED = 5
@@ -97,17 +106,17 @@ BQ_HDN void update(State& S, double beta, double denom, int knew, double* w) {
     double (*bmat)[N] = S.bmat;
     double* vlag = S.vlag;
     double ztest = 0.0;
-    for (int k = 0; k < NPT; k++)
-        for (int j = 0; j < NPTM; j++) ztest = dmax(ztest, fabs(zmat[k][j]));
+    BQ_NOUNROLL for (int k = 0; k < NPT; k++)
+        BQ_NOUNROLL for (int j = 0; j < NPTM; j++) ztest = dmax(ztest, fabs(zmat[k][j]));
     ztest *= 1e-20;
     // rotations that zero the knew-th row of zmat beyond its first column
-    for (int j = 1; j < NPTM; j++) {
+    BQ_NOUNROLL for (int j = 1; j < NPTM; j++) {
         if (fabs(zmat[knew][j]) > ztest) {
             const double a = zmat[knew][0], b = zmat[knew][j];
             double temp = sqrt(a * a + b * b);
             const double tempa = zmat[knew][0] / temp;
             const double tempb = zmat[knew][j] / temp;
-            for (int i = 0; i < NPT; i++) {
+            BQ_NOUNROLL for (int i = 0; i < NPT; i++) {
                 temp = tempa * zmat[i][0] + tempb * zmat[i][j];
                 zmat[i][j] = tempa * zmat[i][j] - tempb * zmat[i][0];
                 zmat[i][0] = temp;
@@ -115,7 +124,7 @@ BQ_HDN void update(State& S, double beta, double denom, int knew, double* w) {
         }
         zmat[knew][j] = 0.0;
     }
-    for (int i = 0; i < NPT; i++) w[i] = zmat[knew][0] * zmat[i][0];
+    BQ_NOUNROLL for (int i = 0; i < NPT; i++) w[i] = zmat[knew][0] * zmat[i][0];
     const double alpha = w[knew];
     const double tau = vlag[knew];
     vlag[knew] -= 1.0;
@@ -123,14 +132,14 @@ BQ_HDN void update(State& S, double beta, double denom, int knew, double* w) {
         const double temp = sqrt(denom);
         const double tempb = zmat[knew][0] / temp;
         const double tempa = tau / temp;
-        for (int i = 0; i < NPT; i++) zmat[i][0] = tempa * zmat[i][0] - tempb * vlag[i];
+        BQ_NOUNROLL for (int i = 0; i < NPT; i++) zmat[i][0] = tempa * zmat[i][0] - tempb * vlag[i];
     }
-    for (int j = 0; j < N; j++) {
+    BQ_NOUNROLL for (int j = 0; j < N; j++) {
         const int jp = NPT + j;
         w[jp] = bmat[knew][j];
         const double tempa = (alpha * vlag[jp] - tau * w[jp]) / denom;
         const double tempb = (-beta * w[jp] - tau * vlag[jp]) / denom;
-        for (int i = 0; i <= jp; i++) {
+        BQ_NOUNROLL for (int i = 0; i <= jp; i++) {
             bmat[i][j] = bmat[i][j] + tempa * vlag[i] + tempb * w[i];
             if (i >= NPT) bmat[jp][i - NPT] = bmat[i][j];
         }
@@ -150,27 +159,27 @@ BQ_HDN void altmov(State& S) {
     const int kopt = S.kopt, knew = S.knew;
     const double adelt = S.adelt;
     const double cnst = 1.0 + sqrt(2.0);
-    for (int k = 0; k < NPT; k++) hcol[k] = 0.0;
-    for (int j = 0; j < NPTM; j++) {
+    BQ_NOUNROLL for (int k = 0; k < NPT; k++) hcol[k] = 0.0;
+    BQ_NOUNROLL for (int j = 0; j < NPTM; j++) {
         const double temp = zmat[knew][j];
-        for (int k = 0; k < NPT; k++) hcol[k] += temp * zmat[k][j];
+        BQ_NOUNROLL for (int k = 0; k < NPT; k++) hcol[k] += temp * zmat[k][j];
     }
     S.alpha = hcol[knew];
     const double ha = 0.5 * S.alpha;
-    for (int i = 0; i < N; i++) glag[i] = bmat[knew][i];
-    for (int k = 0; k < NPT; k++) {
+    BQ_NOUNROLL for (int i = 0; i < N; i++) glag[i] = bmat[knew][i];
+    BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
         double temp = 0.0;
-        for (int j = 0; j < N; j++) temp += xpt[k][j] * xopt[j];
+        BQ_NOUNROLL for (int j = 0; j < N; j++) temp += xpt[k][j] * xopt[j];
         temp = hcol[k] * temp;
-        for (int i = 0; i < N; i++) glag[i] += temp * xpt[k][i];
+        BQ_NOUNROLL for (int i = 0; i < N; i++) glag[i] += temp * xpt[k][i];
     }
     // search along lines through xopt and the other points
     double presav = 0.0, stpsav = 0.0;
     int ksav = 0, ibdsav = 0;
-    for (int k = 0; k < NPT; k++) {
+    BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
         if (k == kopt) continue;
         double dderiv = 0.0, distsq = 0.0;
-        for (int i = 0; i < N; i++) {
+        BQ_NOUNROLL for (int i = 0; i < N; i++) {
             const double temp = xpt[k][i] - xopt[i];
             dderiv += glag[i] * temp;
             distsq += temp * temp;
@@ -179,7 +188,7 @@ BQ_HDN void altmov(State& S) {
         double slbd = -subd;
         int ilbd = 0, iubd = 0;
         const double sumin = dmin(1.0, subd);
-        for (int i = 0; i < N; i++) {
+        BQ_NOUNROLL for (int i = 0; i < N; i++) {
             const double temp = xpt[k][i] - xopt[i];
             if (temp > 0.0) {
                 if (slbd * temp < sl[i] - xopt[i]) { slbd = (sl[i] - xopt[i]) / temp; ilbd = -(i + 1); }
@@ -220,7 +229,7 @@ BQ_HDN void altmov(State& S) {
         const double predsq = vlag * vlag * (vlag * vlag + ha * temp * temp);
         if (predsq > presav) { presav = predsq; ksav = k; stpsav = step; ibdsav = isbd; }
     }
-    for (int i = 0; i < N; i++) {
+    BQ_NOUNROLL for (int i = 0; i < N; i++) {
         const double temp = xopt[i] + stpsav * (xpt[ksav][i] - xopt[i]);
         xnew[i] = dmax(sl[i], dmin(su[i], temp));
     }
@@ -230,9 +239,9 @@ BQ_HDN void altmov(State& S) {
     // constrained Cauchy step, tried for both signs of glag
     const double bigstp = adelt + adelt;
     double csave = 0.0, step = 0.0;
-    for (int iflag = 0; iflag < 2; iflag++) {
+    BQ_NOUNROLL for (int iflag = 0; iflag < 2; iflag++) {
         double wfixsq = 0.0, ggfree = 0.0;
-        for (int i = 0; i < N; i++) {
+        BQ_NOUNROLL for (int i = 0; i < N; i++) {
             wa[i] = 0.0;
             const double tempa = dmin(xopt[i] - sl[i], glag[i]);
             const double tempb = dmax(xopt[i] - su[i], glag[i]);
@@ -245,7 +254,7 @@ BQ_HDN void altmov(State& S) {
             const double wsqsav = wfixsq;
             step = sqrt(temp / ggfree);
             ggfree = 0.0;
-            for (int i = 0; i < N; i++) {
+            BQ_NOUNROLL for (int i = 0; i < N; i++) {
                 if (wa[i] == bigstp) {
                     const double t = xopt[i] - step * glag[i];
                     if (t <= sl[i]) { wa[i] = sl[i] - xopt[i]; wfixsq += wa[i] * wa[i]; }
@@ -256,7 +265,7 @@ BQ_HDN void altmov(State& S) {
             if (!(wfixsq > wsqsav && ggfree > 0.0)) break;
         }
         double gw = 0.0;
-        for (int i = 0; i < N; i++) {
+        BQ_NOUNROLL for (int i = 0; i < N; i++) {
             if (wa[i] == bigstp) {
                 wa[i] = -step * glag[i];
                 xalt[i] = dmax(sl[i], dmin(su[i], xopt[i] + wa[i]));
@@ -266,15 +275,15 @@ BQ_HDN void altmov(State& S) {
             gw += glag[i] * wa[i];
         }
         double curv = 0.0;
-        for (int k = 0; k < NPT; k++) {
+        BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
             double temp = 0.0;
-            for (int j = 0; j < N; j++) temp += xpt[k][j] * wa[j];
+            BQ_NOUNROLL for (int j = 0; j < N; j++) temp += xpt[k][j] * wa[j];
             curv += hcol[k] * temp * temp;
         }
         if (iflag == 1) curv = -curv;
         if (curv > -gw && curv < -cnst * gw) {
             const double scale = -gw / curv;
-            for (int i = 0; i < N; i++) {
+            BQ_NOUNROLL for (int i = 0; i < N; i++) {
                 const double temp = xopt[i] + scale * wa[i];
                 xalt[i] = dmax(sl[i], dmin(su[i], temp));
             }
@@ -285,12 +294,12 @@ BQ_HDN void altmov(State& S) {
             S.cauchy = t * t;
         }
         if (iflag == 0) {
-            for (int i = 0; i < N; i++) { glag[i] = -glag[i]; wa[N + i] = xalt[i]; }
+            BQ_NOUNROLL for (int i = 0; i < N; i++) { glag[i] = -glag[i]; wa[N + i] = xalt[i]; }
             csave = S.cauchy;
         }
     }
     if (csave > S.cauchy) {
-        for (int i = 0; i < N; i++) xalt[i] = wa[N + i];
+        BQ_NOUNROLL for (int i = 0; i < N; i++) xalt[i] = wa[N + i];
         S.cauchy = csave;
     }
 }
@@ -301,20 +310,20 @@ BQ_HDN void altmov(State& S) {
 // ---------------------------------------------------------------------------------------------------------
 BQ_HD void hess_mul(const State& S, const double* s, double* hs) {
     int ih = 0;
-    for (int j = 0; j < N; j++) {
+    BQ_NOUNROLL for (int j = 0; j < N; j++) {
         hs[j] = 0.0;
-        for (int i = 0; i <= j; i++) {
+        BQ_NOUNROLL for (int i = 0; i <= j; i++) {
             if (i < j) hs[j] += S.hq[ih] * s[i];
             hs[i] += S.hq[ih] * s[j];
             ih++;
         }
     }
-    for (int k = 0; k < NPT; k++) {
+    BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
         if (S.pq[k] != 0.0) {
             double temp = 0.0;
-            for (int j = 0; j < N; j++) temp += S.xpt[k][j] * s[j];
+            BQ_NOUNROLL for (int j = 0; j < N; j++) temp += S.xpt[k][j] * s[j];
             temp *= S.pq[k];
-            for (int i = 0; i < N; i++) hs[i] += temp * S.xpt[k][i];
+            BQ_NOUNROLL for (int i = 0; i < N; i++) hs[i] += temp * S.xpt[k][i];
         }
     }
 }
@@ -326,7 +335,7 @@ BQ_HDN void trsbox(State& S) {
     const double delta = S.delta;
     int iterc = 0, nact = 0, itermax = 0, itcsav = 0, iact = 0;
     double gredsq = 0, ggsav = 0, dredsq = 0, dredg = 0, sredg = 0, angbd = 0, xsav = 0, beta = 0, stepsq = 0;
-    for (int i = 0; i < N; i++) {
+    BQ_NOUNROLL for (int i = 0; i < N; i++) {
         xbdi[i] = 0.0;
         if (xopt[i] <= sl[i]) { if (gopt[i] >= 0.0) xbdi[i] = -1.0; }
         else if (xopt[i] >= su[i]) { if (gopt[i] <= 0.0) xbdi[i] = 1.0; }
@@ -347,7 +356,7 @@ BQ_HDN void trsbox(State& S) {
             // fallthrough
         case T_DIRECTION: {
             stepsq = 0.0;
-            for (int i = 0; i < N; i++) {
+            BQ_NOUNROLL for (int i = 0; i < N; i++) {
                 if (xbdi[i] != 0.0) s[i] = 0.0;
                 else if (beta == 0.0) s[i] = -gnew[i];
                 else s[i] = beta * s[i] - gnew[i];
@@ -362,7 +371,7 @@ BQ_HDN void trsbox(State& S) {
         }
         case T_CGSTEP: {
             double resid = delsq, ds = 0.0, shs = 0.0;
-            for (int i = 0; i < N; i++)
+            BQ_NOUNROLL for (int i = 0; i < N; i++)
                 if (xbdi[i] == 0.0) { resid -= d[i] * d[i]; ds += s[i] * d[i]; shs += s[i] * hs[i]; }
             if (resid <= 0.0) { lbl = T_BOUNDARY; break; }
             double temp = sqrt(stepsq * resid + ds * ds);
@@ -372,7 +381,7 @@ BQ_HDN void trsbox(State& S) {
             double stplen = blen;
             if (shs > 0.0) stplen = dmin(blen, gredsq / shs);
             iact = 0;
-            for (int i = 0; i < N; i++) {
+            BQ_NOUNROLL for (int i = 0; i < N; i++) {
                 if (s[i] != 0.0) {
                     const double xsum = xopt[i] + d[i];
                     if (s[i] > 0.0) temp = (su[i] - xsum) / s[i];
@@ -390,7 +399,7 @@ BQ_HDN void trsbox(State& S) {
                 }
                 ggsav = gredsq;
                 gredsq = 0.0;
-                for (int i = 0; i < N; i++) {
+                BQ_NOUNROLL for (int i = 0; i < N; i++) {
                     gnew[i] += stplen * hs[i];
                     if (xbdi[i] == 0.0) gredsq += gnew[i] * gnew[i];
                     d[i] += stplen * s[i];
@@ -423,7 +432,7 @@ BQ_HDN void trsbox(State& S) {
         case T_ALT_PREP: {
             if (nact >= N - 1) { lbl = T_FINISH; break; }
             dredsq = 0.0; dredg = 0.0; gredsq = 0.0;
-            for (int i = 0; i < N; i++) {
+            BQ_NOUNROLL for (int i = 0; i < N; i++) {
                 if (xbdi[i] == 0.0) {
                     dredsq += d[i] * d[i];
                     dredg += d[i] * gnew[i];
@@ -433,7 +442,7 @@ BQ_HDN void trsbox(State& S) {
             }
             itcsav = iterc;
             hess_mul(S, s, hs);
-            for (int i = 0; i < N; i++) hred[i] = hs[i];
+            BQ_NOUNROLL for (int i = 0; i < N; i++) hred[i] = hs[i];
             lbl = T_ALT_DIR;
             break;
         }
@@ -442,7 +451,7 @@ BQ_HDN void trsbox(State& S) {
             double temp = gredsq * dredsq - dredg * dredg;
             if (temp <= qred * 1e-4 * qred) { lbl = T_FINISH; break; }
             temp = sqrt(temp);
-            for (int i = 0; i < N; i++) {
+            BQ_NOUNROLL for (int i = 0; i < N; i++) {
                 if (xbdi[i] == 0.0) s[i] = (dredg * d[i] - dredsq * gnew[i]) / temp;
                 else s[i] = 0.0;
             }
@@ -450,7 +459,7 @@ BQ_HDN void trsbox(State& S) {
             angbd = 1.0;
             iact = 0;
             bool refix = false;
-            for (int i = 0; i < N; i++) {
+            BQ_NOUNROLL for (int i = 0; i < N; i++) {
                 if (xbdi[i] == 0.0) {
                     const double tempa = xopt[i] + d[i] - sl[i];
                     const double tempb = su[i] - xopt[i] - d[i];
@@ -478,12 +487,12 @@ BQ_HDN void trsbox(State& S) {
         }
         case T_ALT_SEARCH: {
             double shs = 0.0, dhs = 0.0, dhd = 0.0;
-            for (int i = 0; i < N; i++)
+            BQ_NOUNROLL for (int i = 0; i < N; i++)
                 if (xbdi[i] == 0.0) { shs += s[i] * hs[i]; dhs += d[i] * hs[i]; dhd += d[i] * hred[i]; }
             double redmax = 0.0, redsav = 0.0, rdprev = 0.0, rdnext = 0.0;
             int isav = 0;
             const int iu = (int)(angbd * 17. + 3.1);
-            for (int i = 1; i <= iu; i++) {
+            BQ_NOUNROLL for (int i = 1; i <= iu; i++) {
                 const double angt = angbd * (double)i / (double)iu;
                 const double sth = (angt + angt) / (1.0 + angt * angt);
                 const double temp = shs + angt * (angt * dhd - dhs - dhs);
@@ -506,7 +515,7 @@ BQ_HDN void trsbox(State& S) {
             const double sdec = sth * (angt * dredg - sredg - 0.5 * sth * temp);
             if (sdec <= 0.0) { lbl = T_FINISH; break; }
             dredg = 0.0; gredsq = 0.0;
-            for (int i = 0; i < N; i++) {
+            BQ_NOUNROLL for (int i = 0; i < N; i++) {
                 gnew[i] = gnew[i] + (cth - 1.0) * hred[i] + sth * hs[i];
                 if (xbdi[i] == 0.0) {
                     d[i] = cth * d[i] + sth * s[i];
@@ -523,7 +532,7 @@ BQ_HDN void trsbox(State& S) {
         }
         case T_FINISH: {
             double dsq = 0.0;
-            for (int i = 0; i < N; i++) {
+            BQ_NOUNROLL for (int i = 0; i < N; i++) {
                 xnew[i] = dmax(dmin(xopt[i] + d[i], su[i]), sl[i]);
                 if (xbdi[i] == -1.0) xnew[i] = sl[i];
                 if (xbdi[i] == 1.0) xnew[i] = su[i];
@@ -540,7 +549,7 @@ BQ_HDN void trsbox(State& S) {
 
 // point handed to the objective: x = clamp(xbase + p) with exact bounds where p sits on sl/su
 BQ_HD void point_from(State& S, const double* p) {
-    for (int i = 0; i < N; i++) {
+    BQ_NOUNROLL for (int i = 0; i < N; i++) {
         S.x[i] = dmin(dmax(S.xl[i], S.xbase[i] + p[i]), S.xu[i]);
         if (p[i] == S.sl[i]) S.x[i] = S.xl[i];
         if (p[i] == S.su[i]) S.x[i] = S.xu[i];
@@ -559,23 +568,23 @@ BQ_HDN void rescue_setup(State& S) {
     const double delta = S.delta;
     const double sfrac = 0.5 / (double)NP;
     double sumpq = 0.0, winc = 0.0;
-    for (int k = 0; k < NPT; k++) {
+    BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
         double distsq = 0.0;
-        for (int j = 0; j < N; j++) { xpt[k][j] -= xopt[j]; distsq += xpt[k][j] * xpt[k][j]; }
+        BQ_NOUNROLL for (int j = 0; j < N; j++) { xpt[k][j] -= xopt[j]; distsq += xpt[k][j] * xpt[k][j]; }
         sumpq += pq[k];
         wr[NDIM + k] = distsq;
         winc = dmax(winc, distsq);
-        for (int j = 0; j < NPTM; j++) zmat[k][j] = 0.0;
+        BQ_NOUNROLL for (int j = 0; j < NPTM; j++) zmat[k][j] = 0.0;
     }
     {
         int ih = 0;
-        for (int j = 0; j < N; j++) {
+        BQ_NOUNROLL for (int j = 0; j < N; j++) {
             wr[j] = 0.5 * sumpq * xopt[j];
-            for (int k = 0; k < NPT; k++) wr[j] += pq[k] * xpt[k][j];
-            for (int i = 0; i <= j; i++) { hq[ih] = hq[ih] + wr[i] * xopt[j] + wr[j] * xopt[i]; ih++; }
+            BQ_NOUNROLL for (int k = 0; k < NPT; k++) wr[j] += pq[k] * xpt[k][j];
+            BQ_NOUNROLL for (int i = 0; i <= j; i++) { hq[ih] = hq[ih] + wr[i] * xopt[j] + wr[j] * xopt[i]; ih++; }
         }
     }
-    for (int j = 0; j < N; j++) {
+    BQ_NOUNROLL for (int j = 0; j < N; j++) {
         S.xbase[j] += xopt[j];
         sl[j] -= xopt[j];
         su[j] -= xopt[j];
@@ -586,11 +595,11 @@ BQ_HDN void rescue_setup(State& S) {
             const double t = ptsaux[2 * j]; ptsaux[2 * j] = ptsaux[2 * j + 1]; ptsaux[2 * j + 1] = t;
         }
         if (fabs(ptsaux[2 * j + 1]) < 0.5 * fabs(ptsaux[2 * j])) ptsaux[2 * j + 1] = 0.5 * ptsaux[2 * j];
-        for (int i = 0; i < NDIM; i++) bmat[i][j] = 0.0;
+        BQ_NOUNROLL for (int i = 0; i < NDIM; i++) bmat[i][j] = 0.0;
     }
     S.fbase_r = S.fval[S.kopt];
     ptsid[0] = sfrac;
-    for (int j = 0; j < N; j++) {
+    BQ_NOUNROLL for (int j = 0; j < N; j++) {
         const int jp = j + 1, jpn = jp + N;   // zero-based rows of the +/- points along e_j
         ptsid[jp] = (double)(j + 1) + sfrac;
         // npt = 2n+1 so jpn < NPT always
@@ -608,8 +617,8 @@ BQ_HDN void rescue_setup(State& S) {
     bool swap_phase = true;
     for (;;) {
         if (swap_phase) {
-            for (int j = 0; j < N; j++) { const double t = bmat[kold][j]; bmat[kold][j] = bmat[knew][j]; bmat[knew][j] = t; }
-            for (int j = 0; j < NPTM; j++) { const double t = zmat[kold][j]; zmat[kold][j] = zmat[knew][j]; zmat[knew][j] = t; }
+            BQ_NOUNROLL for (int j = 0; j < N; j++) { const double t = bmat[kold][j]; bmat[kold][j] = bmat[knew][j]; bmat[knew][j] = t; }
+            BQ_NOUNROLL for (int j = 0; j < NPTM; j++) { const double t = zmat[kold][j]; zmat[kold][j] = zmat[knew][j]; zmat[knew][j] = t; }
             ptsid[kold] = ptsid[knew];
             ptsid[knew] = 0.0;
             wr[NDIM + knew] = 0.0;
@@ -618,23 +627,23 @@ BQ_HDN void rescue_setup(State& S) {
                 const double t = vlag[kold]; vlag[kold] = vlag[knew]; vlag[knew] = t;
                 update(S, beta, denom, knew, wr);   // scratch = rescue's own workspace, as in the original call
                 if (nrem == 0) { S.nrem_r = 0; return; }
-                for (int k = 0; k < NPT; k++) wr[NDIM + k] = fabs(wr[NDIM + k]);
+                BQ_NOUNROLL for (int k = 0; k < NPT; k++) wr[NDIM + k] = fabs(wr[NDIM + k]);
             }
         }
         // pick the original point to reinstate next
         double dsqmin = 0.0;
-        for (int k = 0; k < NPT; k++) {
+        BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
             if (wr[NDIM + k] > 0.0) {
                 if (dsqmin == 0.0 || wr[NDIM + k] < dsqmin) { knew = k; dsqmin = wr[NDIM + k]; }
             }
         }
         if (dsqmin == 0.0) break;
-        for (int j = 0; j < N; j++) wr[NPT + j] = xpt[knew][j];
-        for (int k = 0; k < NPT; k++) {
+        BQ_NOUNROLL for (int j = 0; j < N; j++) wr[NPT + j] = xpt[knew][j];
+        BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
             double sum = 0.0;
             if (k == S.kopt) {
             } else if (ptsid[k] == 0.0) {
-                for (int j = 0; j < N; j++) sum += wr[NPT + j] * xpt[k][j];
+                BQ_NOUNROLL for (int j = 0; j < N; j++) sum += wr[NPT + j] * xpt[k][j];
             } else {
                 const int ip = (int)ptsid[k];
                 if (ip > 0) sum = wr[NPT + ip - 1] * ptsaux[2 * (ip - 1)];
@@ -647,25 +656,25 @@ BQ_HDN void rescue_setup(State& S) {
             }
             wr[k] = 0.5 * sum * sum;
         }
-        for (int k = 0; k < NPT; k++) {
+        BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
             double sum = 0.0;
-            for (int j = 0; j < N; j++) sum += bmat[k][j] * wr[NPT + j];
+            BQ_NOUNROLL for (int j = 0; j < N; j++) sum += bmat[k][j] * wr[NPT + j];
             vlag[k] = sum;
         }
         beta = 0.0;
-        for (int j = 0; j < NPTM; j++) {
+        BQ_NOUNROLL for (int j = 0; j < NPTM; j++) {
             double sum = 0.0;
-            for (int k = 0; k < NPT; k++) sum += zmat[k][j] * wr[k];
+            BQ_NOUNROLL for (int k = 0; k < NPT; k++) sum += zmat[k][j] * wr[k];
             beta -= sum * sum;
-            for (int k = 0; k < NPT; k++) vlag[k] += sum * zmat[k][j];
+            BQ_NOUNROLL for (int k = 0; k < NPT; k++) vlag[k] += sum * zmat[k][j];
         }
         double bsum = 0.0, distsq = 0.0;
-        for (int j = 0; j < N; j++) {
+        BQ_NOUNROLL for (int j = 0; j < N; j++) {
             double sum = 0.0;
-            for (int k = 0; k < NPT; k++) sum += bmat[k][j] * wr[k];
+            BQ_NOUNROLL for (int k = 0; k < NPT; k++) sum += bmat[k][j] * wr[k];
             const int jp = j + NPT;
             bsum += sum * wr[jp];
-            for (int ip = NPT; ip < NDIM; ip++) sum += bmat[ip][j] * wr[ip];
+            BQ_NOUNROLL for (int ip = NPT; ip < NDIM; ip++) sum += bmat[ip][j] * wr[ip];
             bsum += sum * wr[jp];
             vlag[jp] = sum;
             distsq += xpt[knew][j] * xpt[knew][j];
@@ -674,10 +683,10 @@ BQ_HDN void rescue_setup(State& S) {
         vlag[S.kopt] += 1.0;
         denom = 0.0;
         double vlmxsq = 0.0;
-        for (int k = 0; k < NPT; k++) {
+        BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
             if (ptsid[k] != 0.0) {
                 double hdiag = 0.0;
-                for (int j = 0; j < NPTM; j++) hdiag += zmat[k][j] * zmat[k][j];
+                BQ_NOUNROLL for (int j = 0; j < NPTM; j++) hdiag += zmat[k][j] * zmat[k][j];
                 const double den = beta * hdiag + vlag[k] * vlag[k];
                 if (den > denom) { kold = k; denom = den; }
             }
@@ -699,11 +708,11 @@ BQ_HDN void rescue_place(State& S, int kpt) {
     double* hq = S.hq; double* pq = S.pq; double* gopt = S.gopt;
     double* ptsaux = S.w; double* ptsid = S.w + 6; double* wr = S.w + 13;
     int ih = 0;
-    for (int j = 0; j < N; j++) {
+    BQ_NOUNROLL for (int j = 0; j < N; j++) {
         wr[j] = xpt[kpt][j];
         xpt[kpt][j] = 0.0;
         const double temp = pq[kpt] * wr[j];
-        for (int i = 0; i <= j; i++) { hq[ih] += temp * wr[i]; ih++; }
+        BQ_NOUNROLL for (int i = 0; i <= j; i++) { hq[ih] += temp * wr[i]; ih++; }
     }
     pq[kpt] = 0.0;
     const int ip = (int)ptsid[kpt];
@@ -730,7 +739,7 @@ BQ_HDN void rescue_place(State& S, int kpt) {
             vquad += xp * xq * hq[iw - 1];
         }
     }
-    for (int k = 0; k < NPT; k++) {
+    BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
         double temp = 0.0;
         if (ip > 0) temp += xp * xpt[k][ip - 1];
         if (iq > 0) temp += xq * xpt[k][iq - 1];
@@ -747,10 +756,10 @@ BQ_HDN void rescue_absorb(State& S, int kpt, double f) {
     double* hq = S.hq; double* pq = S.pq; double* gopt = S.gopt;
     double* ptsaux = S.w; double* ptsid = S.w + 6;
     const double diff = f - S.vquad_r;
-    for (int i = 0; i < N; i++) gopt[i] += diff * bmat[kpt][i];
-    for (int k = 0; k < NPT; k++) {
+    BQ_NOUNROLL for (int i = 0; i < N; i++) gopt[i] += diff * bmat[kpt][i];
+    BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
         double sum = 0.0;
-        for (int j = 0; j < NPTM; j++) sum += zmat[k][j] * zmat[kpt][j];
+        BQ_NOUNROLL for (int j = 0; j < NPTM; j++) sum += zmat[k][j] * zmat[kpt][j];
         const double temp = diff * sum;
         if (ptsid[k] == 0.0) pq[k] += temp;
         else {
@@ -791,19 +800,19 @@ BQ_HDN int start(State& S, const double* x0, const double* lb, const double* ub,
     S.minf = HUGE_VAL;
     S.in_rescue_from_main = false;
     S.n_rescue = 0;
-    for (int i = 0; i < N; i++) {
+    BQ_NOUNROLL for (int i = 0; i < N; i++) {
         if (lb[i] > ub[i] || x0[i] < lb[i] || x0[i] > ub[i]) { S.rc = R_INVALID_ARGS; S.pc = PC_FINISHED; return DONE; }
     }
     double dx[N];
-    for (int i = 0; i < N; i++) dx[i] = default_step(lb[i], ub[i], x0[i]);
+    BQ_NOUNROLL for (int i = 0; i < N; i++) dx[i] = default_step(lb[i], ub[i], x0[i]);
     // rescale so that all initial steps equal dx[0]  (util/rescale.c:29-44)
-    for (int i = 0; i < N; i++) S.scl[i] = 1.0;
+    BQ_NOUNROLL for (int i = 0; i < N; i++) S.scl[i] = 1.0;
     {
         int i = 1;
-        for (; i < N && dx[i] == dx[i - 1]; ++i) ;
-        if (i < N) for (i = 1; i < N; ++i) S.scl[i] = dx[i] / dx[0];
+        BQ_NOUNROLL for (; i < N && dx[i] == dx[i - 1]; ++i) ;
+        if (i < N) BQ_NOUNROLL for (i = 1; i < N; ++i) S.scl[i] = dx[i] / dx[0];
     }
-    for (int i = 0; i < N; i++) {
+    BQ_NOUNROLL for (int i = 0; i < N; i++) {
         S.x[i] = x0[i] / S.scl[i];
         S.xl[i] = lb[i] / S.scl[i];
         S.xu[i] = ub[i] / S.scl[i];
@@ -812,7 +821,7 @@ BQ_HDN int start(State& S, const double* x0, const double* lb, const double* ub,
     S.rhobeg = fabs(dx[0] / S.scl[0]);
     S.rhoend = xtol_rel * S.rhobeg;   // xtol_abs is zero on this path
     const double rhobeg = S.rhobeg;
-    for (int j = 0; j < N; j++) {
+    BQ_NOUNROLL for (int j = 0; j < N; j++) {
         const double temp = S.xu[j] - S.xl[j];
         if (temp < rhobeg + rhobeg) { S.rc = R_INVALID_ARGS; S.pc = PC_FINISHED; return DONE; }
         S.sl[j] = S.xl[j] - S.x[j];
@@ -826,28 +835,28 @@ BQ_HDN int start(State& S, const double* x0, const double* lb, const double* ub,
         }
     }
     // PRELIM initialisation
-    for (int j = 0; j < N; j++) {
+    BQ_NOUNROLL for (int j = 0; j < N; j++) {
         S.xbase[j] = S.x[j];
-        for (int k = 0; k < NPT; k++) S.xpt[k][j] = 0.0;
-        for (int i = 0; i < NDIM; i++) S.bmat[i][j] = 0.0;
+        BQ_NOUNROLL for (int k = 0; k < NPT; k++) S.xpt[k][j] = 0.0;
+        BQ_NOUNROLL for (int i = 0; i < NDIM; i++) S.bmat[i][j] = 0.0;
     }
-    for (int ih = 0; ih < NH; ih++) S.hq[ih] = 0.0;
-    for (int k = 0; k < NPT; k++) {
+    BQ_NOUNROLL for (int ih = 0; ih < NH; ih++) S.hq[ih] = 0.0;
+    BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
         S.pq[k] = 0.0;
-        for (int j = 0; j < NPTM; j++) S.zmat[k][j] = 0.0;
+        BQ_NOUNROLL for (int j = 0; j < NPTM; j++) S.zmat[k][j] = 0.0;
     }
     S.nf = 0;
     S.pc = PC_PRELIM_EVAL;
     // emit the first point (the base point itself)
     S.nf = 1;
     point_from(S, S.xpt[0]);
-    for (int i = 0; i < N; i++) xs_out[i] = S.x[i] * S.scl[i];
+    BQ_NOUNROLL for (int i = 0; i < N; i++) xs_out[i] = S.x[i] * S.scl[i];
     return ASK;
 }
 
 // final point in the caller's space (bobyqb exit block + unscale)
 BQ_HD void result_x(const State& S, double* xs_out) {
-    for (int i = 0; i < N; i++) xs_out[i] = S.x[i] * S.scl[i];
+    BQ_NOUNROLL for (int i = 0; i < N; i++) xs_out[i] = S.x[i] * S.scl[i];
 }
 
 BQ_HDN int advance(State& S, double f_in, double* xs_out) {
@@ -915,12 +924,12 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
             }
             S.nf = nf2;
             point_from(S, xpt[nf2 - 1]);
-            for (int i = 0; i < N; i++) xs_out[i] = S.x[i] * S.scl[i];
+            BQ_NOUNROLL for (int i = 0; i < N; i++) xs_out[i] = S.x[i] * S.scl[i];
             return ASK;
         }
         // prelim finished (or ran out of evaluations): bobyqb start-up
         S.xoptsq = 0.0;
-        for (int i = 0; i < N; i++) { xopt[i] = xpt[S.kopt][i]; S.xoptsq += xopt[i] * xopt[i]; }
+        BQ_NOUNROLL for (int i = 0; i < N; i++) { xopt[i] = xpt[S.kopt][i]; S.xoptsq += xopt[i] * xopt[i]; }
         S.fsave = fval[0];
         if (stop_evals) { S.rc = R_MAXEVAL_REACHED; lbl = L_EXIT; }
         else {
@@ -962,18 +971,18 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
         case L_GOPT_FIX: {
             if (S.kopt != S.kbase) {
                 int ih = 0;
-                for (int j = 0; j < N; j++)
-                    for (int i = 0; i <= j; i++) {
+                BQ_NOUNROLL for (int j = 0; j < N; j++)
+                    BQ_NOUNROLL for (int i = 0; i <= j; i++) {
                         if (i < j) gopt[j] += hq[ih] * xopt[i];
                         gopt[i] += hq[ih] * xopt[j];
                         ih++;
                     }
                 if (S.nevals > NPT) {
-                    for (int k = 0; k < NPT; k++) {
+                    BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
                         double temp = 0.0;
-                        for (int j = 0; j < N; j++) temp += xpt[k][j] * xopt[j];
+                        BQ_NOUNROLL for (int j = 0; j < N; j++) temp += xpt[k][j] * xopt[j];
                         temp = pq[k] * temp;
-                        for (int i = 0; i < N; i++) gopt[i] += temp * xpt[k][i];
+                        BQ_NOUNROLL for (int i = 0; i < N; i++) gopt[i] += temp * xpt[k][i];
                     }
                 }
             }
@@ -994,13 +1003,13 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
                 if (S.crvmin > 0.0 && errbig > frhosq * S.crvmin) { lbl = L_FARPOINT; break; }
                 const double bdtol = errbig / S.rho;
                 bool far = false;
-                for (int j = 0; j < N; j++) {
+                BQ_NOUNROLL for (int j = 0; j < N; j++) {
                     double bdtest = bdtol;
                     if (xnew[j] == sl[j]) bdtest = w[j];
                     if (xnew[j] == su[j]) bdtest = -w[j];
                     if (bdtest < bdtol) {
                         double curv = hq[hidx(j, j)];
-                        for (int k = 0; k < NPT; k++) curv += pq[k] * (xpt[k][j] * xpt[k][j]);
+                        BQ_NOUNROLL for (int k = 0; k < NPT; k++) curv += pq[k] * (xpt[k][j] * xpt[k][j]);
                         bdtest += 0.5 * curv * S.rho;
                         if (bdtest < bdtol) { far = true; break; }
                     }
@@ -1018,49 +1027,49 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
                 const double xoptsq = S.xoptsq;
                 const double fracsq = xoptsq * .25;
                 double sumpq = 0.0;
-                for (int k = 0; k < NPT; k++) {
+                BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
                     sumpq += pq[k];
                     double sum = -0.5 * xoptsq;
-                    for (int i = 0; i < N; i++) sum += xpt[k][i] * xopt[i];
+                    BQ_NOUNROLL for (int i = 0; i < N; i++) sum += xpt[k][i] * xopt[i];
                     w[NPT + k] = sum;
                     const double temp = fracsq - 0.5 * sum;
-                    for (int i = 0; i < N; i++) {
+                    BQ_NOUNROLL for (int i = 0; i < N; i++) {
                         w[i] = bmat[k][i];
                         vlag[i] = sum * xpt[k][i] + temp * xopt[i];
                         const int ip = NPT + i;
-                        for (int j = 0; j <= i; j++) bmat[ip][j] = bmat[ip][j] + w[i] * vlag[j] + vlag[i] * w[j];
+                        BQ_NOUNROLL for (int j = 0; j <= i; j++) bmat[ip][j] = bmat[ip][j] + w[i] * vlag[j] + vlag[i] * w[j];
                     }
                 }
-                for (int jj = 0; jj < NPTM; jj++) {
+                BQ_NOUNROLL for (int jj = 0; jj < NPTM; jj++) {
                     double sumz = 0.0, sumw = 0.0;
-                    for (int k = 0; k < NPT; k++) {
+                    BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
                         sumz += zmat[k][jj];
                         vlag[k] = w[NPT + k] * zmat[k][jj];
                         sumw += vlag[k];
                     }
-                    for (int j = 0; j < N; j++) {
+                    BQ_NOUNROLL for (int j = 0; j < N; j++) {
                         double sum = (fracsq * sumz - 0.5 * sumw) * xopt[j];
-                        for (int k = 0; k < NPT; k++) sum += vlag[k] * xpt[k][j];
+                        BQ_NOUNROLL for (int k = 0; k < NPT; k++) sum += vlag[k] * xpt[k][j];
                         w[j] = sum;
-                        for (int k = 0; k < NPT; k++) bmat[k][j] += sum * zmat[k][jj];
+                        BQ_NOUNROLL for (int k = 0; k < NPT; k++) bmat[k][j] += sum * zmat[k][jj];
                     }
-                    for (int i = 0; i < N; i++) {
+                    BQ_NOUNROLL for (int i = 0; i < N; i++) {
                         const int ip = i + NPT;
                         const double temp = w[i];
-                        for (int j = 0; j <= i; j++) bmat[ip][j] += temp * w[j];
+                        BQ_NOUNROLL for (int j = 0; j <= i; j++) bmat[ip][j] += temp * w[j];
                     }
                 }
                 int ih = 0;
-                for (int j = 0; j < N; j++) {
+                BQ_NOUNROLL for (int j = 0; j < N; j++) {
                     w[j] = -0.5 * sumpq * xopt[j];
-                    for (int k = 0; k < NPT; k++) { w[j] += pq[k] * xpt[k][j]; xpt[k][j] -= xopt[j]; }
-                    for (int i = 0; i <= j; i++) {
+                    BQ_NOUNROLL for (int k = 0; k < NPT; k++) { w[j] += pq[k] * xpt[k][j]; xpt[k][j] -= xopt[j]; }
+                    BQ_NOUNROLL for (int i = 0; i <= j; i++) {
                         hq[ih] = hq[ih] + w[i] * xopt[j] + xopt[i] * w[j];
                         bmat[NPT + i][j] = bmat[NPT + j][i];
                         ih++;
                     }
                 }
-                for (int i = 0; i < N; i++) {
+                BQ_NOUNROLL for (int i = 0; i < N; i++) {
                     S.xbase[i] += xopt[i];
                     xnew[i] -= xopt[i];
                     sl[i] -= xopt[i];
@@ -1092,13 +1101,13 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
             S.kpt = kpt;
             rescue_place(S, kpt);
             S.pc = PC_RESCUE_EVAL;
-            for (int i = 0; i < N; i++) xs_out[i] = S.x[i] * S.scl[i];
+            BQ_NOUNROLL for (int i = 0; i < N; i++) xs_out[i] = S.x[i] * S.scl[i];
             return ASK;
         }
         case L_RESCUE_DONE: {
             S.xoptsq = 0.0;
             if (S.kopt != S.kbase) {
-                for (int i = 0; i < N; i++) { xopt[i] = xpt[S.kopt][i]; S.xoptsq += xopt[i] * xopt[i]; }
+                BQ_NOUNROLL for (int i = 0; i < N; i++) { xopt[i] = xpt[S.kopt][i]; S.xoptsq += xopt[i] * xopt[i]; }
             }
             if (S.rc != R_SUCCESS) { lbl = L_EXIT; break; }
             S.nresc = S.nevals;
@@ -1110,15 +1119,15 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
         // -------------------------------------------------------------- alternative (geometry) step
         case L_ALTMOV: {
             altmov(S);
-            for (int i = 0; i < N; i++) d[i] = xnew[i] - xopt[i];
+            BQ_NOUNROLL for (int i = 0; i < N; i++) d[i] = xnew[i] - xopt[i];
             lbl = L_VLAG;
             break;
         }
         // -------------------------------------------------------------- Lagrange values, beta, denominator
         case L_VLAG: {
-            for (int k = 0; k < NPT; k++) {
+            BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
                 double suma = 0.0, sumb = 0.0, sum = 0.0;
-                for (int j = 0; j < N; j++) {
+                BQ_NOUNROLL for (int j = 0; j < N; j++) {
                     suma += xpt[k][j] * d[j];
                     sumb += xpt[k][j] * xopt[j];
                     sum += bmat[k][j] * d[j];
@@ -1128,20 +1137,20 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
                 w[NPT + k] = suma;
             }
             double beta = 0.0;
-            for (int jj = 0; jj < NPTM; jj++) {
+            BQ_NOUNROLL for (int jj = 0; jj < NPTM; jj++) {
                 double sum = 0.0;
-                for (int k = 0; k < NPT; k++) sum += zmat[k][jj] * w[k];
+                BQ_NOUNROLL for (int k = 0; k < NPT; k++) sum += zmat[k][jj] * w[k];
                 beta -= sum * sum;
-                for (int k = 0; k < NPT; k++) vlag[k] += sum * zmat[k][jj];
+                BQ_NOUNROLL for (int k = 0; k < NPT; k++) vlag[k] += sum * zmat[k][jj];
             }
             double dsq = 0.0, bsum = 0.0, dx = 0.0;
-            for (int j = 0; j < N; j++) {
+            BQ_NOUNROLL for (int j = 0; j < N; j++) {
                 dsq += d[j] * d[j];
                 double sum = 0.0;
-                for (int k = 0; k < NPT; k++) sum += w[k] * bmat[k][j];
+                BQ_NOUNROLL for (int k = 0; k < NPT; k++) sum += w[k] * bmat[k][j];
                 bsum += sum * d[j];
                 const int jp = NPT + j;
-                for (int i = 0; i < N; i++) sum += bmat[jp][i] * d[i];
+                BQ_NOUNROLL for (int i = 0; i < N; i++) sum += bmat[jp][i] * d[i];
                 vlag[jp] = sum;
                 bsum += sum * d[j];
                 dx += d[j] * xopt[j];
@@ -1154,7 +1163,7 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
                 const double vk = vlag[S.knew];
                 S.denom = vk * vk + S.alpha * beta;
                 if (S.denom < S.cauchy && S.cauchy > 0.0) {
-                    for (int i = 0; i < N; i++) { xnew[i] = xalt[i]; d[i] = xnew[i] - xopt[i]; }
+                    BQ_NOUNROLL for (int i = 0; i < N; i++) { xnew[i] = xalt[i]; d[i] = xnew[i] - xopt[i]; }
                     S.cauchy = 0.0;
                     lbl = L_VLAG;
                     break;
@@ -1169,13 +1178,13 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
                 const double delsq = S.delta * S.delta;
                 double scaden = 0.0, biglsq = 0.0;
                 S.knew = -1;
-                for (int k = 0; k < NPT; k++) {
+                BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
                     if (k == S.kopt) continue;
                     double hdiag = 0.0;
-                    for (int jj = 0; jj < NPTM; jj++) hdiag += zmat[k][jj] * zmat[k][jj];
+                    BQ_NOUNROLL for (int jj = 0; jj < NPTM; jj++) hdiag += zmat[k][jj] * zmat[k][jj];
                     const double den = beta * hdiag + vlag[k] * vlag[k];
                     double distsq = 0.0;
-                    for (int j = 0; j < N; j++) { const double t = xpt[k][j] - xopt[j]; distsq += t * t; }
+                    BQ_NOUNROLL for (int j = 0; j < N; j++) { const double t = xpt[k][j] - xopt[j]; distsq += t * t; }
                     const double r = distsq / delsq;
                     const double temp = dmax(1.0, r * r);
                     if (temp * den > scaden) { scaden = temp * den; S.knew = k; S.denom = den; }
@@ -1196,7 +1205,7 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
             point_from(S, xnew);
             if (S.maxeval > 0 && S.nevals >= S.maxeval) { S.rc = R_MAXEVAL_REACHED; lbl = L_EXIT; break; }
             S.pc = PC_MAIN_EVAL;
-            for (int i = 0; i < N; i++) xs_out[i] = S.x[i] * S.scl[i];
+            BQ_NOUNROLL for (int i = 0; i < N; i++) xs_out[i] = S.x[i] * S.scl[i];
             return ASK;
         }
         case L_AFTER_EVAL: {
@@ -1212,9 +1221,9 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
             double vquad = 0.0;
             {
                 int ih = 0;
-                for (int j = 0; j < N; j++) {
+                BQ_NOUNROLL for (int j = 0; j < N; j++) {
                     vquad += d[j] * gopt[j];
-                    for (int i = 0; i <= j; i++) {
+                    BQ_NOUNROLL for (int i = 0; i <= j; i++) {
                         double temp = d[i] * d[j];
                         if (i == j) temp = 0.5 * temp;
                         vquad += hq[ih] * temp;
@@ -1222,7 +1231,7 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
                     }
                 }
             }
-            for (int k = 0; k < NPT; k++) vquad += 0.5 * pq[k] * (w[NPT + k] * w[NPT + k]);
+            BQ_NOUNROLL for (int k = 0; k < NPT; k++) vquad += 0.5 * pq[k] * (w[NPT + k] * w[NPT + k]);
             const double diff = f - fopt - vquad;
             S.diffc = S.diffb;
             S.diffb = S.diffa;
@@ -1241,12 +1250,12 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
                     const double delsq = S.delta * S.delta;
                     double scaden = 0.0, biglsq = 0.0;
                     S.knew = -1;
-                    for (int k = 0; k < NPT; k++) {
+                    BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
                         double hdiag = 0.0;
-                        for (int jj = 0; jj < NPTM; jj++) hdiag += zmat[k][jj] * zmat[k][jj];
+                        BQ_NOUNROLL for (int jj = 0; jj < NPTM; jj++) hdiag += zmat[k][jj] * zmat[k][jj];
                         const double den = S.beta * hdiag + vlag[k] * vlag[k];
                         double distsq = 0.0;
-                        for (int j = 0; j < N; j++) { const double t = xpt[k][j] - xnew[j]; distsq += t * t; }
+                        BQ_NOUNROLL for (int j = 0; j < N; j++) { const double t = xpt[k][j] - xnew[j]; distsq += t * t; }
                         const double r = distsq / delsq;
                         const double temp = dmax(1.0, r * r);
                         if (temp * den > scaden) { scaden = temp * den; S.knew = k; S.denom = den; }
@@ -1261,68 +1270,68 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
                 int ih = 0;
                 const double pqold = pq[knew];
                 pq[knew] = 0.0;
-                for (int i = 0; i < N; i++) {
+                BQ_NOUNROLL for (int i = 0; i < N; i++) {
                     const double temp = pqold * xpt[knew][i];
-                    for (int j = 0; j <= i; j++) { hq[ih] += temp * xpt[knew][j]; ih++; }
+                    BQ_NOUNROLL for (int j = 0; j <= i; j++) { hq[ih] += temp * xpt[knew][j]; ih++; }
                 }
             }
-            for (int jj = 0; jj < NPTM; jj++) {
+            BQ_NOUNROLL for (int jj = 0; jj < NPTM; jj++) {
                 const double temp = diff * zmat[knew][jj];
-                for (int k = 0; k < NPT; k++) pq[k] += temp * zmat[k][jj];
+                BQ_NOUNROLL for (int k = 0; k < NPT; k++) pq[k] += temp * zmat[k][jj];
             }
             fval[knew] = f;
-            for (int i = 0; i < N; i++) { xpt[knew][i] = xnew[i]; w[i] = bmat[knew][i]; }
+            BQ_NOUNROLL for (int i = 0; i < N; i++) { xpt[knew][i] = xnew[i]; w[i] = bmat[knew][i]; }
             bool singular = false;
-            for (int k = 0; k < NPT; k++) {
+            BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
                 double suma = 0.0;
-                for (int jj = 0; jj < NPTM; jj++) suma += zmat[knew][jj] * zmat[k][jj];
+                BQ_NOUNROLL for (int jj = 0; jj < NPTM; jj++) suma += zmat[knew][jj] * zmat[k][jj];
                 if (isinf(suma)) { singular = true; break; }
                 double sumb = 0.0;
-                for (int j = 0; j < N; j++) sumb += xpt[k][j] * xopt[j];
+                BQ_NOUNROLL for (int j = 0; j < N; j++) sumb += xpt[k][j] * xopt[j];
                 const double temp = suma * sumb;
-                for (int i = 0; i < N; i++) w[i] += temp * xpt[k][i];
+                BQ_NOUNROLL for (int i = 0; i < N; i++) w[i] += temp * xpt[k][i];
             }
             if (singular) { S.rc = R_ROUNDOFF_LIMITED; lbl = L_EXIT; break; }
-            for (int i = 0; i < N; i++) gopt[i] += diff * w[i];
+            BQ_NOUNROLL for (int i = 0; i < N; i++) gopt[i] += diff * w[i];
             if (f < fopt) {
                 S.kopt = knew;
                 S.xoptsq = 0.0;
                 int ih = 0;
-                for (int j = 0; j < N; j++) {
+                BQ_NOUNROLL for (int j = 0; j < N; j++) {
                     xopt[j] = xnew[j];
                     S.xoptsq += xopt[j] * xopt[j];
-                    for (int i = 0; i <= j; i++) {
+                    BQ_NOUNROLL for (int i = 0; i <= j; i++) {
                         if (i < j) gopt[j] += hq[ih] * d[i];
                         gopt[i] += hq[ih] * d[j];
                         ih++;
                     }
                 }
-                for (int k = 0; k < NPT; k++) {
+                BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
                     double temp = 0.0;
-                    for (int j = 0; j < N; j++) temp += xpt[k][j] * d[j];
+                    BQ_NOUNROLL for (int j = 0; j < N; j++) temp += xpt[k][j] * d[j];
                     temp = pq[k] * temp;
-                    for (int i = 0; i < N; i++) gopt[i] += temp * xpt[k][i];
+                    BQ_NOUNROLL for (int i = 0; i < N; i++) gopt[i] += temp * xpt[k][i];
                 }
                 // nlopt_stop_ftol never fires here: ftol_rel = ftol_abs = 0 on this path (util/stop.c:28-34)
             }
             if (S.ntrits > 0) {
                 // least Frobenius norm interpolant test
-                for (int k = 0; k < NPT; k++) { vlag[k] = fval[k] - fval[S.kopt]; w[k] = 0.0; }
-                for (int j = 0; j < NPTM; j++) {
+                BQ_NOUNROLL for (int k = 0; k < NPT; k++) { vlag[k] = fval[k] - fval[S.kopt]; w[k] = 0.0; }
+                BQ_NOUNROLL for (int j = 0; j < NPTM; j++) {
                     double sum = 0.0;
-                    for (int k = 0; k < NPT; k++) sum += zmat[k][j] * vlag[k];
-                    for (int k = 0; k < NPT; k++) w[k] += sum * zmat[k][j];
+                    BQ_NOUNROLL for (int k = 0; k < NPT; k++) sum += zmat[k][j] * vlag[k];
+                    BQ_NOUNROLL for (int k = 0; k < NPT; k++) w[k] += sum * zmat[k][j];
                 }
-                for (int k = 0; k < NPT; k++) {
+                BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
                     double sum = 0.0;
-                    for (int j = 0; j < N; j++) sum += xpt[k][j] * xopt[j];
+                    BQ_NOUNROLL for (int j = 0; j < N; j++) sum += xpt[k][j] * xopt[j];
                     w[k + NPT] = w[k];
                     w[k] = sum * w[k];
                 }
                 double gqsq = 0.0, gisq = 0.0;
-                for (int i = 0; i < N; i++) {
+                BQ_NOUNROLL for (int i = 0; i < N; i++) {
                     double sum = 0.0;
-                    for (int k = 0; k < NPT; k++) sum = sum + bmat[k][i] * vlag[k] + xpt[k][i] * w[k];
+                    BQ_NOUNROLL for (int k = 0; k < NPT; k++) sum = sum + bmat[k][i] * vlag[k] + xpt[k][i] * w[k];
                     if (xopt[i] == sl[i]) {
                         const double a = dmin(0.0, gopt[i]); gqsq += a * a;
                         const double b = dmin(0.0, sum); gisq += b * b;
@@ -1338,9 +1347,9 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
                 ++S.itest;
                 if (gqsq < 10.0 * gisq) S.itest = 0;
                 if (S.itest >= 3) {
-                    for (int i = 0; i < N; i++) gopt[i] = vlag[NPT + i];
-                    for (int k = 0; k < NPT; k++) pq[k] = w[NPT + k];
-                    for (int ih = 0; ih < NH; ih++) hq[ih] = 0.0;
+                    BQ_NOUNROLL for (int i = 0; i < N; i++) gopt[i] = vlag[NPT + i];
+                    BQ_NOUNROLL for (int k = 0; k < NPT; k++) pq[k] = w[NPT + k];
+                    BQ_NOUNROLL for (int ih = 0; ih < NH; ih++) hq[ih] = 0.0;
                     S.itest = 0;
                 }
             }
@@ -1356,9 +1365,9 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
         // -------------------------------------------------------------- is some point too far from xopt?
         case L_FARPOINT: {
             S.knew = -1;
-            for (int k = 0; k < NPT; k++) {
+            BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
                 double sum = 0.0;
-                for (int j = 0; j < N; j++) { const double t = xpt[k][j] - xopt[j]; sum += t * t; }
+                BQ_NOUNROLL for (int j = 0; j < N; j++) { const double t = xpt[k][j] - xopt[j]; sum += t * t; }
                 if (sum > S.distsq) { S.knew = k; S.distsq = sum; }
             }
             if (S.knew >= 0) {

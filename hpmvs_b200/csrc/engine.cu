@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -74,6 +75,7 @@ struct hpmvs_engine {
     unsigned long long launches = 0;
     size_t smem_bytes = 0;
     int blocks_per_sm = 0;
+    int force_lanes = 0;
     std::mutex mu;
 };
 
@@ -130,6 +132,7 @@ static hp::KParams make_params(hpmvs_engine* e, const hpmvs_patch_t* d_in, hpmvs
     K.n = n;
     K.work_counter = e->d_work;
     K.counters = e->d_counters;
+    K.lanes_per_warp = 1;
     return K;
 }
 
@@ -174,6 +177,7 @@ int hpmvs_engine_create(const hpmvs_options_t* opt, int device, hpmvs_engine_t**
     HP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->blocks_per_sm, hp::optimize_kernel, hp::WARPS_PER_BLOCK * 32,
                                                           e->smem_bytes));
     if (e->blocks_per_sm < 1) e->blocks_per_sm = 1;
+    if (const char* fl = getenv("HPMVS_FORCE_LANES")) e->force_lanes = atoi(fl);
     *out = e;
     return 0;
 }
@@ -340,11 +344,18 @@ static int launch_optimize(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, hp
     rc = sync_cameras(e);
     if (rc) return rc;
     HP_CUDA(cudaMemsetAsync(e->d_work, 0, sizeof(int), s));
-    const hp::KParams K = make_params(e, d_in, d_out, n);
+    hp::KParams K = make_params(e, d_in, d_out, n);
     const int warps = hp::WARPS_PER_BLOCK;
-    int grid = e->sm_count * e->blocks_per_sm;            // persistent: every resident warp slot, a multiple of the SM count
+    // persistent grid: every resident block slot of every SM (a multiple of the SM count).  Each warp keeps
+    // `lanes` patches in flight; small batches are spread over all warps first (lanes < 32) so that no SM idles.
+    int grid = e->sm_count * e->blocks_per_sm;
     const int need = (n + warps - 1) / warps;
     if (need < grid) grid = need > 0 ? need : 1;
+    int lanes = (n + grid * warps - 1) / (grid * warps);
+    if (lanes < 1) lanes = 1;
+    if (lanes > 32) lanes = 32;
+    if (e->force_lanes > 0) lanes = e->force_lanes;
+    K.lanes_per_warp = lanes;
     HP_CUDA(cudaEventRecord(e->ev0, s));
     hp::optimize_kernel<<<grid, warps * 32, e->smem_bytes, s>>>(K);
     HP_CUDA(cudaEventRecord(e->ev1, s));

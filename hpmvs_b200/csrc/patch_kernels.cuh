@@ -1,12 +1,19 @@
-// Device code of the hpmvs_b200 engine (sm_100a).  One warp owns one patch at a time and runs the whole of
-// PatchOptimizer::optimize() for it (/root/reference/src/hpmvs/PatchOptimizer.cpp:48-103):
-//   * lane 0 ("leader") executes the scalar control logic: view-list edits and the FP64 BOBYQA state machine
-//     (bobyqa3.h), whose state lives in the warp's shared-memory slab;
-//   * all 32 lanes execute the photometric work co-operatively: per-view projection set-up (lane = view),
-//     7x7 bilinear RGB sampling (lane = sample), and the mean / variance / correlation reductions, which are
-//     evaluated as SEQUENTIAL f32 chains (lane = texture) so that every rounding matches the reference's
-//     scalar loops (Patch2d.hpp:37-84) - that is what makes the BOBYQA trajectory reproducible.
-// Warps pull patches from a global atomic counter (persistent kernel) because the work per patch varies 10x.
+// Device code of the hpmvs_b200 engine (sm_100a): everything below PatchOptimizer::optimize()
+// (/root/reference/src/hpmvs/PatchOptimizer.cpp:48-103) for a batch of patches, in one persistent kernel.
+//
+// Work decomposition ("lane = patch for control, warp = patch for pixels"):
+//   * every warp keeps up to 32 patches in flight, one per lane slot.  The FP64 BOBYQA state machine
+//     (bobyqa3.h, ~1.6 KB of state per patch, thread-private => local memory) advances for all of a warp's
+//     patches at once in SIMT fashion, so its long scalar instruction stream is amortised over the lanes;
+//   * whenever patches need their photometric objective, the warp serves them one after the other with all
+//     32 lanes co-operating: per-view projection set-up (lane = view), 7x7 bilinear RGB sampling
+//     (lane = sample) and the mean / variance / correlation reductions, which are evaluated as SEQUENTIAL f32
+//     chains (lane = texture) so that every rounding matches the reference's scalar loops
+//     (Patch2d.hpp:37-84) - that is what makes the BOBYQA trajectory reproducible bit for bit;
+//   * the short view-list stages before and after the refinement (addImages, filterImagesNCC, sortImages,
+//     setRefImage, ...) also run warp-co-operatively on the patch's context in shared memory.
+// Warps pull patches from a global atomic counter (the work per patch varies by 10x) and refill a lane slot
+// as soon as its patch retires.
 //
 // Compile with -fmad=false: every f32/f64 expression below is written in the reference's evaluation order and
 // must not be contracted into FMAs.
@@ -55,6 +62,7 @@ struct KParams {
     int n;
     int* work_counter;
     unsigned long long* counters;   // patches, ok, evals, textures
+    int lanes_per_warp;             // patches kept in flight per warp (1..32)
 };
 
 struct ViewSetup {
@@ -64,30 +72,40 @@ struct ViewSetup {
     const uchar4* img;
 };
 
-struct __align__(16) WarpShared {
-    bq3::State bq;
+// per-warp scratch for one photometric evaluation
+struct __align__(16) Scratch {
     float tex[VC][TEXS];
     float q[VC][QS];
     float mean[VC][4];
     float sigma[VC];
     int slot_view[VC];
-    float center[4], normal[4];
-    float refCenter[4], refRay[4];
-    float X0[4], Y0[4], Z0[4];
     float rays[MAXV][4];
     ViewSetup vs[MAXV];
     float dots[MAXV];
     float incc[MAXV];
     float tmp_f[MAXV];
     int tmp_i[MAXV];
-    int images[MAXV];
     int vlist[MAXV];
     unsigned char vvalid[MAXV];
-    double xcur[3];
-    float scale;
-    int nimg;
+};
+
+// per-lane-slot patch context (shared memory): what the co-operative stages read and write for one patch
+struct __align__(16) LaneCtx {
+    float center[4], normal[4];          // pCenter_, pNormal_
+    float refCenter[4], refRay[4];       // refCenter_, refRay_
+    float X0[4], Y0[4], Z0[4];           // imgX_[0], imgY_[0], imgZ_[0]
+    double score;
+    float scale;                         // pScale_
+    int nimg;                            // pImages_.size()
     int textures;
-    int action;
+    int patch_index;
+    int status, nlopt_rc, evals, pad;
+    unsigned short images[MAXV];         // pImages_
+};
+
+struct __align__(16) WarpShared {
+    Scratch S;
+    LaneCtx ctx[32];
 };
 
 // ----------------------------------------------------------------------------------------------------------
@@ -207,7 +225,7 @@ __device__ __forceinline__ bool view_setup(const KParams& K, const DevCamera& ca
 }
 
 // sampleTexture part 2 (:509-525): 49 samples, lane = sample (two passes); raw RGB goes to tex[slot]
-__device__ __forceinline__ void sample_view(WarpShared& W, int slot, int k, int lane) {
+__device__ __forceinline__ void sample_view(Scratch& W, int slot, int k, int lane) {
     const ViewSetup v = W.vs[k];
     float* t = W.tex[slot];
 #pragma unroll
@@ -228,7 +246,7 @@ __device__ __forceinline__ void sample_view(WarpShared& W, int slot, int k, int 
 }
 
 // PatchTex::normalize (Patch2d.hpp:46-84) for slots [first, first+ns): sequential chains, lane = (slot,channel)
-__device__ __forceinline__ void normalize_slots(WarpShared& W, int first, int ns, int lane) {
+__device__ __forceinline__ void normalize_slots(Scratch& W, int first, int ns, int lane) {
     __syncwarp();
     if (lane < 3 * ns) {
         const int slot = first + lane / 3, ch = lane % 3;
@@ -269,7 +287,7 @@ __device__ __forceinline__ void normalize_slots(WarpShared& W, int first, int ns
 }
 
 // PatchTex::dot (Patch2d.hpp:37-44) of slot 0 with slots [1, 1+no): lane = slot for the 147-term chain
-__device__ __forceinline__ void dot_slots(WarpShared& W, int no, int lane) {
+__device__ __forceinline__ void dot_slots(Scratch& W, int no, int lane) {
     for (int idx = lane; idx < no * TEXN; idx += 32) {
         const int so = idx / TEXN, i = idx - TEXN * so, slot = 1 + so;
         W.tex[slot][i] = W.tex[0][i] * W.tex[slot][i];
@@ -288,22 +306,22 @@ __device__ __forceinline__ void dot_slots(WarpShared& W, int no, int lane) {
 
 // ----------------------------------------------------------------------------------------------------------
 // The photometric core shared by objective_fn (:286-311) and setINCCs (:448-474):
-// for the current W.center / W.normal / W.scale and view list, with view `refIdx` as reference, fill
+// for patch context P (centre / normal / scale / view list) with view `refIdx` as reference, fill
 // W.vvalid[k] (sampleTexture succeeded) and W.dots[k] = refTex.dot(tex_k) for every valid k != refIdx.
 // If the reference view itself fails nothing else is sampled (both callers return early).
 // ----------------------------------------------------------------------------------------------------------
-__device__ __noinline__ void eval_dots(WarpShared& W, const KParams& K, int lane, int refIdx, bool z_is_normal) {
-    const int nimg = W.nimg;
-    const f4 c = ld4(W.center);
-    const f4 n = ld4(W.normal);
-    const float scale = W.scale;
+__device__ __noinline__ void eval_dots(Scratch& W, LaneCtx& P, const KParams& K, int lane, int refIdx, bool z_is_normal) {
+    const int nimg = P.nimg;
+    const f4 c = ld4(P.center);
+    const f4 n = ld4(P.normal);
+    const float scale = P.scale;
     f4 xa, ya, za;
-    patch_axes(K.cams[W.images[refIdx]], n, scale, xa, ya, za);
+    patch_axes(K.cams[P.images[refIdx]], n, scale, xa, ya, za);
     const f4 zgate = z_is_normal ? n : za;     // setINCCs passes pNormal_, objective_fn passes pZaxis_ (:456 vs :292)
     bool ok = false;
     if (lane < nimg) {
         ViewSetup vs;
-        ok = view_setup(K, K.cams[W.images[lane]], c, scale, xa, ya, zgate, vs);
+        ok = view_setup(K, K.cams[P.images[lane]], c, scale, xa, ya, zgate, vs);
         if (ok) W.vs[lane] = vs;
         W.vvalid[lane] = ok ? 1 : 0;
     }
@@ -314,7 +332,7 @@ __device__ __noinline__ void eval_dots(WarpShared& W, const KParams& K, int lane
     const unsigned omask = vmask & ~(1u << refIdx);
     if (ok && lane != refIdx) W.vlist[__popc(omask & ((1u << lane) - 1u))] = lane;
     const int nother = __popc(omask);
-    if (lane == 0) W.textures += 1 + nother;
+    if (lane == 0) P.textures += 1 + nother;
     __syncwarp();
     // reference texture -> slot 0, then the others in groups of VC-1
     int done = 0;
@@ -336,11 +354,12 @@ __device__ __noinline__ void eval_dots(WarpShared& W, const KParams& K, int lane
 }
 
 // objective_fn's reduction (:294-310), evaluated identically by every lane from shared values
-__device__ __forceinline__ double objective_value(const WarpShared& W, const KParams& K) {
+__device__ __forceinline__ double objective_value(const Scratch& W, const LaneCtx& P, const KParams& K) {
     if (!W.vvalid[0]) return 2.0;
     double val = 0.0;
     int nImgs = 0;
-    for (int ii = 1; ii < W.nimg; ii++) {
+    const int nimg = P.nimg;
+    for (int ii = 1; ii < nimg; ii++) {
         if (!W.vvalid[ii]) continue;
         const float r = (float)(1.0 - (double)W.dots[ii]);
         val += (double)(r / (1.0f + 3.0f * r));
@@ -351,9 +370,9 @@ __device__ __forceinline__ double objective_value(const WarpShared& W, const KPa
 }
 
 // setINCCs (:448-474): lane = view
-__device__ __forceinline__ void set_inccs(WarpShared& W, const KParams& K, int lane, int refIdx, int robust) {
-    eval_dots(W, K, lane, refIdx, true);
-    if (lane < W.nimg) {
+__device__ __forceinline__ void set_inccs(Scratch& W, LaneCtx& P, const KParams& K, int lane, int refIdx, int robust) {
+    eval_dots(W, P, K, lane, refIdx, true);
+    if (lane < P.nimg) {
         float v;
         if (!W.vvalid[refIdx]) v = 2.0f;
         else if (lane == refIdx) v = 0.0f;
@@ -368,32 +387,33 @@ __device__ __forceinline__ void set_inccs(WarpShared& W, const KParams& K, int l
 }
 
 // ordered compaction of the view list: keep[lane] for lane < nimg
-__device__ __forceinline__ void compact_images(WarpShared& W, int lane, bool keep) {
-    const int n = W.nimg;
-    const int img = (lane < n) ? W.images[lane] : 0;
+__device__ __forceinline__ void compact_images(LaneCtx& P, int lane, bool keep) {
+    const int n = P.nimg;
+    const int img = (lane < n) ? P.images[lane] : 0;
     const unsigned mask = __ballot_sync(FULL, keep && lane < n);
     __syncwarp();
-    if (keep && lane < n) W.images[__popc(mask & ((1u << lane) - 1u))] = img;
-    if (lane == 0) W.nimg = __popc(mask);
+    if (keep && lane < n) P.images[__popc(mask & ((1u << lane) - 1u))] = (unsigned short)img;
+    if (lane == 0) P.nimg = __popc(mask);
     __syncwarp();
 }
 
 // filterImagesNCC (:138-152)
-__device__ __forceinline__ bool filter_images_ncc(WarpShared& W, const KParams& K, int lane, float threshold) {
-    set_inccs(W, K, lane, 0, 0);
-    const bool keep = (lane == 0) || (lane < W.nimg && W.incc[lane] < 1.0f - threshold);
+__device__ __forceinline__ bool filter_images_ncc(Scratch& W, LaneCtx& P, const KParams& K, int lane, float threshold) {
+    set_inccs(W, P, K, lane, 0, 0);
+    const bool keep = (lane == 0) || (lane < P.nimg && W.incc[lane] < 1.0f - threshold);
     __syncwarp();
-    compact_images(W, lane, keep);
-    return W.nimg >= K.opt.min_images_per_patch;
+    compact_images(P, lane, keep);
+    return P.nimg >= K.opt.min_images_per_patch;
 }
 
 // addImages (:225-258).  Returns 1 ok, 0 fail, -1 view list overflow.
-__device__ __forceinline__ int add_images(WarpShared& W, const KParams& K, int lane) {
-    if (W.nimg <= 0) return 0;
-    const int ref = W.images[0];
-    const int n0 = W.nimg;
+__device__ __forceinline__ int add_images(LaneCtx& P, const KParams& K, int lane) {
+    if (P.nimg <= 0) return 0;
+    const int ref = P.images[0];
+    const int n0 = P.nimg;
     const int beg = K.covis_off[ref], end = K.covis_off[ref + 1];
-    const f4 c = ld4(W.center), nrm = ld4(W.normal);
+    const f4 c = ld4(P.center), nrm = ld4(P.normal);
+    const float scale = P.scale;
     int count = n0;
     for (int base = beg; base < end; base += 32) {
         const int j = base + lane;
@@ -402,7 +422,7 @@ __device__ __forceinline__ int add_images(WarpShared& W, const KParams& K, int l
         if (j < end) {
             cand = K.covis_ids[j];
             keep = true;
-            for (int i = 0; i < n0; i++) if (W.images[i] == cand) keep = false;
+            for (int i = 0; i < n0; i++) if (P.images[i] == cand) keep = false;
             if (keep) {
                 const DevCamera& cam = K.cams[cand];
                 const f4 d = sub4(ld4(cam.center), c);
@@ -412,7 +432,7 @@ __device__ __forceinline__ int add_images(WarpShared& W, const KParams& K, int l
                 if (z > 0.0f) r = f4{d.x / fz, d.y / fz, d.z / fz, d.w / fz};
                 if (dot4(r, nrm) < K.cos_max_f) keep = false;
                 if (keep) {
-                    const int lvl = (int)roundf(level_from(cam, fz, W.scale));
+                    const int lvl = (int)roundf(level_from(cam, fz, scale));
                     if (lvl < K.opt.minlevel || lvl >= K.opt.maxlevel - 2) keep = false;
                     if (keep) {
                         float u, v;
@@ -424,20 +444,20 @@ __device__ __forceinline__ int add_images(WarpShared& W, const KParams& K, int l
         }
         const unsigned mask = __ballot_sync(FULL, keep);
         const int pos = count + __popc(mask & ((1u << lane) - 1u));
-        if (keep && pos < MAXV) W.images[pos] = cand;
+        if (keep && pos < MAXV) P.images[pos] = (unsigned short)cand;
         count += __popc(mask);
     }
     __syncwarp();
     if (count > MAXV) return -1;
-    if (lane == 0) W.nimg = count;
+    if (lane == 0) P.nimg = count;
     __syncwarp();
     return count >= K.opt.min_images_per_patch ? 1 : 0;
 }
 
 // rays[i] = (cam_i.center - center).normalized() for all views; lane = view
-__device__ __forceinline__ f4 view_ray(const WarpShared& W, const KParams& K, int lane, float* fz_out) {
-    const DevCamera& cam = K.cams[W.images[lane]];
-    const f4 d = sub4(ld4(cam.center), ld4(W.center));
+__device__ __forceinline__ f4 view_ray(const LaneCtx& P, const KParams& K, int lane, float* fz_out) {
+    const DevCamera& cam = K.cams[P.images[lane]];
+    const f4 d = sub4(ld4(cam.center), ld4(P.center));
     const float z = dot4(d, d);
     const float fz = sqrtf(z);
     if (fz_out) *fz_out = fz;
@@ -446,25 +466,25 @@ __device__ __forceinline__ f4 view_ray(const WarpShared& W, const KParams& K, in
 }
 
 // sortImages + getAngleWeightedScales (:183-223, :260-284).  Return value is ignored by the reference (:54).
-__device__ __forceinline__ void sort_images(WarpShared& W, const KParams& K, int lane) {
-    const int nimg = W.nimg;
+__device__ __forceinline__ void sort_images(Scratch& W, LaneCtx& P, const KParams& K, int lane) {
+    const int nimg = P.nimg;
     if (nimg == 0) return;
     float fz0;
     {
-        const DevCamera& cam0 = K.cams[W.images[0]];
-        const f4 d = sub4(ld4(W.center), ld4(cam0.center));
+        const DevCamera& cam0 = K.cams[P.images[0]];
+        const f4 d = sub4(ld4(P.center), ld4(cam0.center));
         fz0 = sqrtf(dot4(d, d));
     }
-    const int refLevel = max(0, min(K.opt.maxlevel - 1, (int)roundf(level_from(K.cams[W.images[0]], fz0, W.scale))));
+    const int refLevel = max(0, min(K.opt.maxlevel - 1, (int)roundf(level_from(K.cams[P.images[0]], fz0, P.scale))));
     bool keep = false;
     f4 ray = f4{0, 0, 0, 0};
     float ws = 0.0f;
     int img = 0;
     if (lane < nimg) {
-        img = W.images[lane];
+        img = P.images[lane];
         float fz;
-        ray = view_ray(W, K, lane, &fz);
-        const float cosa = dot4(ray, normalized4(ld4(W.normal)));
+        ray = view_ray(P, K, lane, &fz);
+        const float cosa = dot4(ray, normalized4(ld4(P.normal)));
         if (cosa > 0.0f) {
             keep = true;
             const DevCamera& cam = K.cams[img];
@@ -492,7 +512,7 @@ __device__ __forceinline__ void sort_images(WarpShared& W, const KParams& K, int
                 int index = 0;
                 float best = W.tmp_f[0];
                 for (int j = 1; j < m; j++) if (W.tmp_f[j] < best) { best = W.tmp_f[j]; index = j; }
-                W.images[out++] = W.tmp_i[index];
+                P.images[out++] = (unsigned short)W.tmp_i[index];
                 const f4 ri = ld4(W.rays[index]);
                 int jj = 0;
                 for (int j = 0; j < m; j++) {
@@ -508,16 +528,16 @@ __device__ __forceinline__ void sort_images(WarpShared& W, const KParams& K, int
                 m = jj;
             }
         }
-        W.nimg = out;   // pImages_.clear() happens before the size test (:190-193)
+        P.nimg = out;   // pImages_.clear() happens before the size test (:190-193)
     }
     __syncwarp();
 }
 
 // assureImageAngles (:105-123)
-__device__ __forceinline__ bool assure_image_angles(WarpShared& W, const KParams& K, int lane) {
-    const int nimg = W.nimg;
+__device__ __forceinline__ bool assure_image_angles(Scratch& W, LaneCtx& P, const KParams& K, int lane) {
+    const int nimg = P.nimg;
     if (lane < nimg) {
-        const f4 r = view_ray(W, K, lane, nullptr);
+        const f4 r = view_ray(P, K, lane, nullptr);
         W.rays[lane][0] = r.x; W.rays[lane][1] = r.y; W.rays[lane][2] = r.z; W.rays[lane][3] = r.w;
     }
     __syncwarp();
@@ -537,41 +557,42 @@ __device__ __forceinline__ bool assure_image_angles(WarpShared& W, const KParams
 }
 
 // filterImagesByAngle (:125-136)
-__device__ __forceinline__ bool filter_images_by_angle(WarpShared& W, const KParams& K, int lane) {
+__device__ __forceinline__ bool filter_images_by_angle(LaneCtx& P, const KParams& K, int lane) {
     bool keep = false;
-    if (lane < W.nimg) {
-        const f4 r = view_ray(W, K, lane, nullptr);
-        keep = dot4(r, ld4(W.normal)) > K.cos_max_f;
+    if (lane < P.nimg) {
+        const f4 r = view_ray(P, K, lane, nullptr);
+        keep = dot4(r, ld4(P.normal)) > K.cos_max_f;
     }
-    compact_images(W, lane, keep);
-    return W.nimg >= K.opt.min_images_per_patch;
+    __syncwarp();
+    compact_images(P, lane, keep);
+    return P.nimg >= K.opt.min_images_per_patch;
 }
 
 // setRefImage (:154-181)
-__device__ __forceinline__ void set_ref_image(WarpShared& W, const KParams& K, int lane) {
-    const int nimg = W.nimg;
+__device__ __forceinline__ void set_ref_image(Scratch& W, LaneCtx& P, const KParams& K, int lane) {
+    const int nimg = P.nimg;
     if (nimg <= 1) return;
     int refindex = -1;
     float refncc = 3.402823466e+38f;
     for (int ii = 0; ii < nimg; ii++) {
-        set_inccs(W, K, lane, ii, 1);
+        set_inccs(W, P, K, lane, ii, 1);
         float sum = 0.0f;
         for (int k = 0; k < nimg; k++) sum = sum + W.incc[k];
         if (sum < refncc) { refncc = sum; refindex = ii; }
         __syncwarp();
     }
     if (lane == 0 && refindex > 0) {
-        const int t = W.images[0];
-        W.images[0] = W.images[refindex];
-        W.images[refindex] = t;
+        const unsigned short t = P.images[0];
+        P.images[0] = P.images[refindex];
+        P.images[refindex] = t;
     }
     __syncwarp();
 }
 
-// setCenterNorm (:401-414): leader writes center / normal for parameters x
-__device__ __forceinline__ void set_center_norm(WarpShared& W, const KParams& K, const double* x) {
+// setCenterNorm (:401-414): the owning lane writes its patch's centre / normal for parameters x
+__device__ __forceinline__ void set_center_norm(LaneCtx& P, const KParams& K, const double* x) {
     const float x0 = (float)x[0];
-    for (int i = 0; i < 4; i++) W.center[i] = W.refCenter[i] + (x0 * W.refRay[i]) * 1.0f;
+    for (int i = 0; i < 4; i++) P.center[i] = P.refCenter[i] + (x0 * P.refRay[i]) * 1.0f;
     const float angle1 = (float)(x[1] * (double)K.angle_scale);
     const float angle2 = (float)(x[2] * (double)K.angle_scale);
     double s1, c1, s2, c2;
@@ -580,24 +601,24 @@ __device__ __forceinline__ void set_center_norm(WarpShared& W, const KParams& K,
     const float fx = (float)(s1 * c2);
     const float fy = (float)s2;
     const float fz = (float)(-c1 * c2);
-    for (int i = 0; i < 3; i++) W.normal[i] = (W.X0[i] * fx + W.Y0[i] * fy) + W.Z0[i] * fz;
-    W.normal[3] = 0.0f;
+    for (int i = 0; i < 3; i++) P.normal[i] = (P.X0[i] * fx + P.Y0[i] * fy) + P.Z0[i] * fz;
+    P.normal[3] = 0.0f;
 }
 
-// setOptimizationFields + parametersFromCenterNorm (:384-399, :416-446): leader only
-__device__ __forceinline__ void init_parameters(WarpShared& W, const KParams& K, const double* lb, const double* ub, double* x) {
-    const DevCamera& cam = K.cams[W.images[0]];
-    for (int i = 0; i < 3; i++) { W.X0[i] = cam.nx[i]; W.Y0[i] = cam.ny[i]; W.Z0[i] = cam.nz[i]; }
-    for (int i = 0; i < 4; i++) W.refCenter[i] = W.center[i];
-    const f4 rr = normalized4(sub4(ld4(W.refCenter), ld4(cam.center)));
-    W.refRay[0] = rr.x; W.refRay[1] = rr.y; W.refRay[2] = rr.z; W.refRay[3] = rr.w;
+// setOptimizationFields + parametersFromCenterNorm (:384-399, :416-446): owning lane only
+__device__ __forceinline__ void init_parameters(LaneCtx& P, const KParams& K, const double* lb, const double* ub, double* x) {
+    const DevCamera& cam = K.cams[P.images[0]];
+    for (int i = 0; i < 3; i++) { P.X0[i] = cam.nx[i]; P.Y0[i] = cam.ny[i]; P.Z0[i] = cam.nz[i]; }
+    for (int i = 0; i < 4; i++) P.refCenter[i] = P.center[i];
+    const f4 rr = normalized4(sub4(ld4(P.refCenter), ld4(cam.center)));
+    P.refRay[0] = rr.x; P.refRay[1] = rr.y; P.refRay[2] = rr.z; P.refRay[3] = rr.w;
     // c == refCenter here, so x[0] = 0 . refRay / depthScale
-    x[0] = (double)(dot4(sub4(ld4(W.center), ld4(W.refCenter)), rr) / 1.0f);
-    const f3 n3 = f3{W.normal[0], W.normal[1], W.normal[2]};
-    const float fx = dot3(f3{W.X0[0], W.X0[1], W.X0[2]}, n3);
-    const float fy = dot3(f3{W.Y0[0], W.Y0[1], W.Y0[2]}, n3);
-    const float fz = dot3(f3{W.Z0[0], W.Z0[1], W.Z0[2]}, n3);
-    x[2] = (double)(float)asin((double)fy);                       // std::asin(float)
+    x[0] = (double)(dot4(sub4(ld4(P.center), ld4(P.refCenter)), rr) / 1.0f);
+    const f3 n3 = f3{P.normal[0], P.normal[1], P.normal[2]};
+    const float fx = dot3(f3{P.X0[0], P.X0[1], P.X0[2]}, n3);
+    const float fy = dot3(f3{P.Y0[0], P.Y0[1], P.Y0[2]}, n3);
+    const float fz = dot3(f3{P.Z0[0], P.Z0[1], P.Z0[2]}, n3);
+    x[2] = (double)(float)asin((double)fy);                       // std::asin(float), correctly rounded
     const float cosb = (float)cos(fmax(-1.0, fmin(1.0, x[2])));
     if (cosb == 0.0f) x[1] = 0.0;
     else {
@@ -611,56 +632,17 @@ __device__ __forceinline__ void init_parameters(WarpShared& W, const KParams& K,
     for (int i = 0; i < 3; i++) x[i] = fmin(ub[i], fmax(lb[i], x[i]));
 }
 
-// optimizePatch (:322-382)
-__device__ __noinline__ int optimize_patch(WarpShared& W, const KParams& K, int lane, int& nlopt_rc, int& evals, double& score) {
-    nlopt_rc = 0; evals = 0; score = 0.0;
-    if (W.nimg < K.opt.min_images_per_patch) return HPMVS_FAIL_OPT_MINIMAGES;
-    if (lane == 0) {
-        const double lb[3] = {-HUGE_VAL, -23.99999, -23.99999};
-        const double ub[3] = {HUGE_VAL, 23.99999, 23.99999};
-        double x0[3];
-        init_parameters(W, K, lb, ub, x0);
-        W.action = bq3::start(W.bq, x0, lb, ub, 1.e-7, 1000, W.xcur);
-        if (W.action == bq3::ASK) set_center_norm(W, K, W.xcur);
-    }
-    __syncwarp();
-    while (W.action == bq3::ASK) {
-        eval_dots(W, K, lane, 0, false);
-        if (lane == 0) {
-            const double f = objective_value(W, K);
-            W.action = bq3::advance(W.bq, f, W.xcur);
-            if (W.action == bq3::ASK) set_center_norm(W, K, W.xcur);
-        }
-        __syncwarp();
-    }
-    nlopt_rc = W.bq.rc;
-    evals = W.bq.nevals;
-    score = W.bq.minf;
-    const bool success = (nlopt_rc >= 1 && nlopt_rc <= 4);
-    if (!success) {
-        return nlopt_rc == bq3::R_ROUNDOFF_LIMITED ? HPMVS_FAIL_OPT_ROUNDOFF
-               : nlopt_rc == bq3::R_MAXEVAL_REACHED ? HPMVS_FAIL_OPT_MAXEVAL : HPMVS_FAIL_OPT_OTHER;
-    }
-    if (lane == 0) {
-        double xf[3];
-        bq3::result_x(W.bq, xf);
-        set_center_norm(W, K, xf);
-    }
-    __syncwarp();
-    return HPMVS_OK;
-}
-
 // Scene::getColor(const Patch3d&) (Scene.cpp:300-327): lane = view; stable rank by colour norm
-__device__ __forceinline__ f3 patch_color(WarpShared& W, const KParams& K, int lane) {
-    const int nimg = W.nimg;
+__device__ __forceinline__ f3 patch_color(Scratch& W, LaneCtx& P, const KParams& K, int lane) {
+    const int nimg = P.nimg;
     f3 col = f3{0, 0, 0};
     float nrm = 0.0f;
     if (lane < nimg) {
-        const DevCamera& cam = K.cams[W.images[lane]];
-        const f4 c = ld4(W.center);
+        const DevCamera& cam = K.cams[P.images[lane]];
+        const f4 c = ld4(P.center);
         const f4 d = sub4(c, ld4(cam.center));
         const float fz = sqrtf(dot4(d, d));
-        const int lvl = leveli_from(cam, fz, W.scale, cam.nlevels - 1);
+        const int lvl = leveli_from(cam, fz, P.scale, cam.nlevels - 1);
         float u, v;
         project(cam, c, lvl, u, v);
         col = get_color(cam.img[lvl], cam.pitch[lvl], u, v);
@@ -688,78 +670,166 @@ __device__ __forceinline__ f3 patch_color(WarpShared& W, const KParams& K, int l
     return o;
 }
 
-__device__ __forceinline__ void load_patch(WarpShared& W, const hpmvs_patch_t& p, int lane) {
-    if (lane < 4) { W.center[lane] = p.center[lane]; W.normal[lane] = p.normal[lane]; }
-    if (lane == 0) { W.scale = p.scale; W.nimg = min(max(p.nimages, 0), MAXV); W.textures = 0; }
-    W.images[lane] = p.images[lane];
+__device__ __forceinline__ void load_patch(LaneCtx& P, const hpmvs_patch_t& p, int pi, int lane) {
+    if (lane < 4) { P.center[lane] = p.center[lane]; P.normal[lane] = p.normal[lane]; }
+    if (lane == 0) {
+        P.scale = p.scale; P.nimg = min(max(p.nimages, 0), MAXV); P.textures = 0; P.patch_index = pi;
+        P.status = HPMVS_OK; P.nlopt_rc = 0; P.evals = 0; P.score = 0.0;
+    }
+    P.images[lane] = (unsigned short)p.images[lane];
     __syncwarp();
 }
 
-// runOptimization (:48-76); returns the status code
-__device__ __forceinline__ int run_patch(WarpShared& W, const KParams& K, int lane, int& nlopt_rc, int& evals, double& score) {
-    nlopt_rc = 0; evals = 0; score = 0.0;
-    int r = add_images(W, K, lane);
+// runOptimization (:48-57): the stages before the refinement.  Returns HPMVS_OK when the patch may be refined.
+__device__ __noinline__ int pre_stage(Scratch& W, LaneCtx& P, const KParams& K, int lane) {
+    const int r = add_images(P, K, lane);
     if (r < 0) return HPMVS_FAIL_TOO_MANY_VIEWS;
     if (r == 0) return HPMVS_FAIL_ADD_IMAGES;
-    if (!filter_images_ncc(W, K, lane, K.opt.ncc_alpha_1)) return HPMVS_FAIL_NCC1;
-    sort_images(W, K, lane);
-    if (!assure_image_angles(W, K, lane)) return HPMVS_FAIL_ANGLES;
-    const int st = optimize_patch(W, K, lane, nlopt_rc, evals, score);
-    if (st != HPMVS_OK) return st;
-    r = add_images(W, K, lane);
-    if (r < 0) return HPMVS_FAIL_TOO_MANY_VIEWS;
-    if (r == 0) return HPMVS_FAIL_ADD_IMAGES2;
-    if (!filter_images_ncc(W, K, lane, K.opt.ncc_alpha_2)) return HPMVS_FAIL_NCC2;
-    if (!filter_images_by_angle(W, K, lane)) return HPMVS_FAIL_ANGLE_FILTER;
-    if (!assure_image_angles(W, K, lane)) return HPMVS_FAIL_ANGLES2;
-    set_ref_image(W, K, lane);
-    if (!filter_images_ncc(W, K, lane, K.opt.ncc_alpha_2)) return HPMVS_FAIL_NCC3;
+    if (!filter_images_ncc(W, P, K, lane, K.opt.ncc_alpha_1)) return HPMVS_FAIL_NCC1;
+    sort_images(W, P, K, lane);
+    if (!assure_image_angles(W, P, K, lane)) return HPMVS_FAIL_ANGLES;
+    if (P.nimg < K.opt.min_images_per_patch) return HPMVS_FAIL_OPT_MINIMAGES;   // optimizePatch (:323)
     return HPMVS_OK;
 }
 
+// runOptimization (:62-75): the stages after a successful refinement
+__device__ __noinline__ int post_stage(Scratch& W, LaneCtx& P, const KParams& K, int lane) {
+    const int r = add_images(P, K, lane);
+    if (r < 0) return HPMVS_FAIL_TOO_MANY_VIEWS;
+    if (r == 0) return HPMVS_FAIL_ADD_IMAGES2;
+    if (!filter_images_ncc(W, P, K, lane, K.opt.ncc_alpha_2)) return HPMVS_FAIL_NCC2;
+    if (!filter_images_by_angle(P, K, lane)) return HPMVS_FAIL_ANGLE_FILTER;
+    if (!assure_image_angles(W, P, K, lane)) return HPMVS_FAIL_ANGLES2;
+    set_ref_image(W, P, K, lane);
+    if (!filter_images_ncc(W, P, K, lane, K.opt.ncc_alpha_2)) return HPMVS_FAIL_NCC3;
+    return HPMVS_OK;
+}
+
+// write one result record (PatchOptimizer.cpp:86-100); all lanes of the warp participate
+__device__ __forceinline__ void retire_patch(Scratch& W, LaneCtx& P, const KParams& K, int lane, int status) {
+    const int pi = P.patch_index;
+    const hpmvs_patch_t& pin = K.in[pi];
+    hpmvs_patch_t& po = K.out[pi];
+    if (status == HPMVS_OK) {
+        const f3 col = patch_color(W, P, K, lane);
+        if (lane < 4) { po.center[lane] = P.center[lane]; po.normal[lane] = P.normal[lane]; }
+        po.images[lane] = (lane < P.nimg) ? (int)P.images[lane] : 0;
+        if (lane == 0) {
+            po.scale = P.scale; po.nimages = P.nimg;
+            po.color[0] = col.x; po.color[1] = col.y; po.color[2] = col.z;
+            po.ncc = 1.4f;
+        }
+    } else {
+        // rejected: geometry and view list stay as given (PatchOptimizer.cpp:86-93 runs only on success)
+        if (lane < 4) { po.center[lane] = pin.center[lane]; po.normal[lane] = pin.normal[lane]; }
+        po.images[lane] = pin.images[lane];
+        if (lane == 0) {
+            po.scale = pin.scale; po.nimages = pin.nimages;
+            po.color[0] = 0.0f; po.color[1] = 0.0f; po.color[2] = 0.0f;
+            po.ncc = 0.0f;
+        }
+    }
+    if (lane == 0) {
+        po.status = status; po.nlopt_result = P.nlopt_rc; po.evals = P.evals; po.textures = P.textures; po.score = P.score;
+    }
+    __syncwarp();
+}
+
 // ----------------------------------------------------------------------------------------------------------
-// K2: the fused optimize kernel.  Persistent warps, dynamic work distribution.
+// K2: the fused optimize kernel.  Persistent warps, up to 32 patches in flight per warp.
 // ----------------------------------------------------------------------------------------------------------
+enum : int { SLOT_IDLE = 0, SLOT_NEW = 1, SLOT_ACTIVE = 2, SLOT_FINISHED = 3 };
+
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) optimize_kernel(const KParams K) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    WarpShared& W = reinterpret_cast<WarpShared*>(smem_raw)[threadIdx.x >> 5];
+    WarpShared& WS = reinterpret_cast<WarpShared*>(smem_raw)[threadIdx.x >> 5];
+    Scratch& W = WS.S;
     const int lane = threadIdx.x & 31;
+    LaneCtx& mine = WS.ctx[lane];
+    bq3::State bq;                       // this lane's optimiser (local memory)
+    double xcur[3] = {0.0, 0.0, 0.0};
+    double fcur = 0.0;
+    int slot = SLOT_IDLE;
+    bool queue_empty = false;
     unsigned long long c_ok = 0, c_evals = 0, c_tex = 0, c_n = 0;
+    const unsigned lane_quota = (K.lanes_per_warp >= 32) ? FULL : ((1u << K.lanes_per_warp) - 1u);
+
     for (;;) {
-        int pi = 0;
-        if (lane == 0) pi = atomicAdd(K.work_counter, 1);
-        pi = __shfl_sync(FULL, pi, 0);
-        if (pi >= K.n) break;
-        const hpmvs_patch_t& pin = K.in[pi];
-        load_patch(W, pin, lane);
-        int nlopt_rc, evals;
-        double score;
-        const int status = run_patch(W, K, lane, nlopt_rc, evals, score);
-        hpmvs_patch_t& po = K.out[pi];
-        if (status == HPMVS_OK) {
-            const f3 col = patch_color(W, K, lane);
-            if (lane < 4) { po.center[lane] = W.center[lane]; po.normal[lane] = W.normal[lane]; }
-            po.images[lane] = (lane < W.nimg) ? W.images[lane] : 0;
-            if (lane == 0) {
-                po.scale = W.scale; po.nimages = W.nimg;
-                po.color[0] = col.x; po.color[1] = col.y; po.color[2] = col.z;
-                po.ncc = 1.4f;
+        // ---- 1. refill idle lane slots: fetch a patch and run its pre-stage co-operatively -----------------
+        unsigned idle = __ballot_sync(FULL, slot == SLOT_IDLE) & lane_quota;
+        while (idle && !queue_empty) {
+            const int l = __ffs(idle) - 1;
+            int pi = 0;
+            if (lane == 0) pi = atomicAdd(K.work_counter, 1);
+            pi = __shfl_sync(FULL, pi, 0);
+            if (pi >= K.n) { queue_empty = true; break; }
+            LaneCtx& P = WS.ctx[l];
+            load_patch(P, K.in[pi], pi, lane);
+            const int st = pre_stage(W, P, K, lane);
+            if (st != HPMVS_OK) {
+                retire_patch(W, P, K, lane, st);
+                if (lane == 0) { c_n++; c_tex += P.textures; }
+                continue;                        // same slot, next patch
             }
-        } else {
-            // rejected: geometry and view list stay as given (PatchOptimizer.cpp:86-93 runs only on success)
-            if (lane < 4) { po.center[lane] = pin.center[lane]; po.normal[lane] = pin.normal[lane]; }
-            po.images[lane] = pin.images[lane];
-            if (lane == 0) {
-                po.scale = pin.scale; po.nimages = pin.nimages;
-                po.color[0] = 0.0f; po.color[1] = 0.0f; po.color[2] = 0.0f;
-                po.ncc = 0.0f;
-            }
+            if (lane == l) slot = SLOT_NEW;
+            idle &= idle - 1;
         }
-        if (lane == 0) {
-            po.status = status; po.nlopt_result = nlopt_rc; po.evals = evals; po.textures = W.textures; po.score = score;
-            c_n++; c_ok += (status == HPMVS_OK); c_evals += evals; c_tex += W.textures;
+        // ---- 2. start the optimiser of freshly filled slots (lane-parallel) --------------------------------
+        if (slot == SLOT_NEW) {
+            const double lb[3] = {-HUGE_VAL, -23.99999, -23.99999};
+            const double ub[3] = {HUGE_VAL, 23.99999, 23.99999};
+            double x0[3];
+            init_parameters(mine, K, lb, ub, x0);
+            const int act = bq3::start(bq, x0, lb, ub, 1.e-7, 1000, xcur);
+            if (act == bq3::ASK) { set_center_norm(mine, K, xcur); slot = SLOT_ACTIVE; }
+            else slot = SLOT_FINISHED;
         }
         __syncwarp();
+        unsigned active = __ballot_sync(FULL, slot == SLOT_ACTIVE);
+        unsigned finished = __ballot_sync(FULL, slot == SLOT_FINISHED);
+        if (!active && !finished) break;         // nothing in flight and the queue is empty
+        // ---- 3. objective for every active slot, one after the other, all lanes co-operating ---------------
+        for (unsigned m = active; m; m &= m - 1) {
+            const int l = __ffs(m) - 1;
+            LaneCtx& P = WS.ctx[l];
+            eval_dots(W, P, K, lane, 0, false);
+            const double f = objective_value(W, P, K);
+            if (lane == l) fcur = f;
+            __syncwarp();
+        }
+        // ---- 4. advance every active optimiser (lane-parallel SIMT) ----------------------------------------
+        if (slot == SLOT_ACTIVE) {
+            const int act = bq3::advance(bq, fcur, xcur);
+            if (act == bq3::ASK) set_center_norm(mine, K, xcur);
+            else slot = SLOT_FINISHED;
+        }
+        if (slot == SLOT_FINISHED) {
+            // optimizePatch's epilogue (:364-381)
+            const int rc = bq.rc;
+            mine.nlopt_rc = rc; mine.evals = bq.nevals; mine.score = bq.minf;
+            if (rc >= 1 && rc <= 4) {
+                double xf[3];
+                bq3::result_x(bq, xf);
+                set_center_norm(mine, K, xf);
+                mine.status = HPMVS_OK;
+            } else {
+                mine.status = rc == bq3::R_ROUNDOFF_LIMITED ? HPMVS_FAIL_OPT_ROUNDOFF
+                              : rc == bq3::R_MAXEVAL_REACHED ? HPMVS_FAIL_OPT_MAXEVAL : HPMVS_FAIL_OPT_OTHER;
+            }
+        }
+        __syncwarp();
+        // ---- 5. retire finished slots: post-stage + colour + result record, co-operatively ------------------
+        finished = __ballot_sync(FULL, slot == SLOT_FINISHED);
+        for (unsigned m = finished; m; m &= m - 1) {
+            const int l = __ffs(m) - 1;
+            LaneCtx& P = WS.ctx[l];
+            int st = P.status;
+            if (st == HPMVS_OK) st = post_stage(W, P, K, lane);
+            retire_patch(W, P, K, lane, st);
+            if (lane == 0) { c_n++; c_ok += (st == HPMVS_OK); c_evals += P.evals; c_tex += P.textures; }
+            __syncwarp();
+        }
+        if (slot == SLOT_FINISHED) slot = SLOT_IDLE;
     }
     if (lane == 0 && c_n) {
         atomicAdd(&K.counters[0], c_n); atomicAdd(&K.counters[1], c_ok);
@@ -772,20 +842,22 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) optimize_kernel(const KP
 // ----------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) ncc_kernel(const KParams K, int ref_idx, int robust, float* inccs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    WarpShared& W = reinterpret_cast<WarpShared*>(smem_raw)[threadIdx.x >> 5];
+    WarpShared& WS = reinterpret_cast<WarpShared*>(smem_raw)[threadIdx.x >> 5];
+    Scratch& W = WS.S;
+    LaneCtx& P = WS.ctx[0];
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     unsigned long long c_tex = 0;
     for (int pi = warp; pi < K.n; pi += nwarps) {
-        load_patch(W, K.in[pi], lane);
+        load_patch(P, K.in[pi], pi, lane);
         float v = 2.0f;
-        if (ref_idx < W.nimg) {
-            set_inccs(W, K, lane, ref_idx, robust);
-            if (lane < W.nimg) v = W.incc[lane];
+        if (ref_idx < P.nimg) {
+            set_inccs(W, P, K, lane, ref_idx, robust);
+            if (lane < P.nimg) v = W.incc[lane];
         }
-        inccs[(size_t)pi * MAXV + lane] = (lane < W.nimg) ? v : 0.0f;
-        if (lane == 0) c_tex += W.textures;
+        inccs[(size_t)pi * MAXV + lane] = (lane < P.nimg) ? v : 0.0f;
+        if (lane == 0) c_tex += P.textures;
         __syncwarp();
     }
     if (lane == 0 && c_tex) atomicAdd(&K.counters[3], c_tex);

@@ -23,6 +23,7 @@ for i in range(len(seeds)):
         bad += 1
         if bad < 4: print("ncc mismatch", i, r, g[i, :len(r)])
 print("K1 setINCCs mismatches:", bad, "of", len(seeds))
+oracle.set_cr_asinf(os.environ.get('ORC_CR','1')=='1')
 t = time.time(); ref = orc.optimize_batch(seeds, nthreads=8); t_cpu = time.time() - t
 t = time.time(); got = eng.optimize(pe); t_gpu = time.time() - t
 print("cpu %.3fs gpu %.3fs kernel %.3f ms" % (t_cpu, t_gpu, eng.last_kernel_ms()))
