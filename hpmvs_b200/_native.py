@@ -19,7 +19,7 @@ HEADERS = [os.path.join(_HERE, "csrc", "patch_kernels.cuh"), os.path.join(_HERE,
 # -fmad=false / -ffp-contract=off: the kernels restate the reference's f32/f64 evaluation order (see
 # patch_kernels.cuh); FMA contraction would change roundings and break the reproducible BOBYQA trajectory.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-              "-Xcompiler", "-fPIC,-ffp-contract=off", "-diag-suppress", "550", "-shared"]
+              "-Xcompiler", "-fPIC,-ffp-contract=off", "-diag-suppress", "550,177", "-shared"]
 
 
 def _stale() -> bool:
@@ -34,7 +34,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    extra = ["-DHP_PROFILE"] if os.environ.get("HPMVS_BUILD_PROFILE") else []
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)

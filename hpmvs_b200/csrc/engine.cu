@@ -73,11 +73,25 @@ struct hpmvs_engine {
     int* d_work = nullptr;
     unsigned long long* d_counters = nullptr;
     unsigned long long launches = 0;
-    size_t smem_bytes = 0;
+    size_t smem_bytes = 0, smem_opt_bytes = 0;
     int blocks_per_sm = 0;
     int force_lanes = 0;
+    int variant = 0;
     std::mutex mu;
 };
+
+// Instantiated CTA shapes of the fused kernel: (optimizer warps, sampler warps).  The default is picked from
+// measurements; HPMVS_CONFIG="ow,sw" selects another one for experiments.
+struct KernelVariant {
+    int ow, sw, lpw;
+    void (*fn)(const hp::KParams);
+    size_t smem;
+};
+#define HP_VARIANT(OW, SW, LPW) {OW, SW, LPW, hp::optimize_kernel<OW, SW, LPW>, sizeof(hp::CtaSharedT<OW, SW, LPW>)}
+static const KernelVariant g_variants[] = {HP_VARIANT(2, 10, 32), HP_VARIANT(2, 8, 32), HP_VARIANT(2, 6, 32), HP_VARIANT(4, 8, 16),
+                                           HP_VARIANT(4, 10, 16), HP_VARIANT(8, 8, 8), HP_VARIANT(8, 10, 8), HP_VARIANT(4, 12, 12),
+                                           HP_VARIANT(6, 10, 10), HP_VARIANT(1, 8, 32), HP_VARIANT(3, 10, 20)};
+static const int g_default_variant = 0;
 
 static int ensure_patch_capacity(hpmvs_engine* e, size_t n) {
     if (n <= e->cap_patches) return 0;
@@ -169,12 +183,20 @@ int hpmvs_engine_create(const hpmvs_options_t* opt, int device, hpmvs_engine_t**
     HP_CUDA(cudaEventCreate(&e->ev0));
     HP_CUDA(cudaEventCreate(&e->ev1));
     HP_CUDA(cudaMalloc(&e->d_work, sizeof(int)));
-    HP_CUDA(cudaMalloc(&e->d_counters, 4 * sizeof(unsigned long long)));
-    HP_CUDA(cudaMemset(e->d_counters, 0, 4 * sizeof(unsigned long long)));
-    e->smem_bytes = sizeof(hp::WarpShared) * hp::WARPS_PER_BLOCK;
-    HP_CUDA(cudaFuncSetAttribute(hp::optimize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    HP_CUDA(cudaMalloc(&e->d_counters, 16 * sizeof(unsigned long long)));
+    HP_CUDA(cudaMemset(e->d_counters, 0, 16 * sizeof(unsigned long long)));
+    e->smem_bytes = sizeof(hp::WarpShared) * hp::WARPS_PER_BLOCK;          // ncc_kernel
+    e->variant = g_default_variant;
+    if (const char* cfg = getenv("HPMVS_CONFIG")) {
+        int ow = 0, sw = 0, lpw = 0;
+        if (sscanf(cfg, "%d,%d,%d", &ow, &sw, &lpw) == 3)
+            for (size_t i = 0; i < sizeof(g_variants) / sizeof(g_variants[0]); i++)
+                if (g_variants[i].ow == ow && g_variants[i].sw == sw && g_variants[i].lpw == lpw) e->variant = (int)i;
+    }
+    e->smem_opt_bytes = g_variants[e->variant].smem;                        // optimize_kernel: one CTA per SM
+    HP_CUDA(cudaFuncSetAttribute(g_variants[e->variant].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_opt_bytes));
     HP_CUDA(cudaFuncSetAttribute(hp::ncc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
-    HP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->blocks_per_sm, hp::optimize_kernel, hp::WARPS_PER_BLOCK * 32,
+    HP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->blocks_per_sm, hp::ncc_kernel, hp::WARPS_PER_BLOCK * 32,
                                                           e->smem_bytes));
     if (e->blocks_per_sm < 1) e->blocks_per_sm = 1;
     if (const char* fl = getenv("HPMVS_FORCE_LANES")) e->force_lanes = atoi(fl);
@@ -345,19 +367,19 @@ static int launch_optimize(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, hp
     if (rc) return rc;
     HP_CUDA(cudaMemsetAsync(e->d_work, 0, sizeof(int), s));
     hp::KParams K = make_params(e, d_in, d_out, n);
-    const int warps = hp::WARPS_PER_BLOCK;
-    // persistent grid: every resident block slot of every SM (a multiple of the SM count).  Each warp keeps
-    // `lanes` patches in flight; small batches are spread over all warps first (lanes < 32) so that no SM idles.
-    int grid = e->sm_count * e->blocks_per_sm;
-    const int need = (n + warps - 1) / warps;
-    if (need < grid) grid = need > 0 ? need : 1;
-    int lanes = (n + grid * warps - 1) / (grid * warps);
+    // persistent grid: one warp-specialised CTA per SM.  Each optimizer warp keeps `lanes` patches in flight;
+    // small batches are spread over all SMs first (lanes < 32) so that no SM idles.
+    const KernelVariant& V = g_variants[e->variant];
+    const int slots_per_cta = V.ow;                                // x lanes
+    int grid = e->sm_count;
+    if (n < grid * slots_per_cta) grid = (n + slots_per_cta - 1) / slots_per_cta;
+    int lanes = (n + grid * slots_per_cta - 1) / (grid * slots_per_cta);
     if (lanes < 1) lanes = 1;
-    if (lanes > 32) lanes = 32;
+    if (lanes > V.lpw) lanes = V.lpw;
     if (e->force_lanes > 0) lanes = e->force_lanes;
     K.lanes_per_warp = lanes;
     HP_CUDA(cudaEventRecord(e->ev0, s));
-    hp::optimize_kernel<<<grid, warps * 32, e->smem_bytes, s>>>(K);
+    V.fn<<<grid, (V.ow + V.sw) * 32, e->smem_opt_bytes, s>>>(K);
     HP_CUDA(cudaEventRecord(e->ev1, s));
     e->launches++;
     HP_CUDA(cudaGetLastError());
@@ -427,9 +449,11 @@ int hpmvs_engine_counters(hpmvs_engine_t* e, hpmvs_counters_t* out, int reset) {
     if (!e || !out) return HPMVS_E_ARG;
     std::lock_guard<std::mutex> lk(e->mu);
     HP_CUDA(cudaSetDevice(e->device));
-    unsigned long long c[4];
+    unsigned long long c[16];
     HP_CUDA(cudaStreamSynchronize(e->stream));
     HP_CUDA(cudaMemcpy(c, e->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+    if (getenv("HPMVS_PROFILE_PRINT"))
+        fprintf(stderr, "[hpmvs profile] opt: wait %llu adv %llu rounds %llu lanes %llu | sampler: idle %llu eval %llu n_eval %llu\n", c[4], c[5], c[6], c[7], c[8], c[9], c[10]);
     out->patches = c[0]; out->patches_ok = c[1]; out->evals = c[2]; out->textures = c[3];
     out->kernel_launches = e->launches;
     if (reset) {

@@ -35,6 +35,13 @@ constexpr int QS = 52;
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr unsigned FULL = 0xffffffffu;
 
+// -DHP_PROFILE adds HP_CLOCK() accounting of optimizer / sampler time to counters[4..10] (see engine.cu)
+#ifdef HP_PROFILE
+#define HP_CLOCK() clock64()
+#else
+#define HP_CLOCK() 0ll
+#endif
+
 struct DevCamera {
     float P[HPMVS_LEVELS][12];
     float center[4];
@@ -736,104 +743,238 @@ __device__ __forceinline__ void retire_patch(Scratch& W, LaneCtx& P, const KPara
 }
 
 // ----------------------------------------------------------------------------------------------------------
-// K2: the fused optimize kernel.  Persistent warps, up to 32 patches in flight per warp.
+// K2: the fused optimize kernel.  One persistent, warp-specialised CTA per SM:
+//   * OPT_WARPS "optimizer" warps: lane = patch slot.  Each lane owns one in-flight patch and its FP64 BOBYQA
+//     state (thread-private, local memory) and advances it in SIMT fashion.  The optimiser's large, branchy
+//     instruction stream is therefore fetched by very few warps per SM.
+//   * SAMPLER_WARPS "sampler" warps: serve requests from a shared-memory ticket queue with all 32 lanes
+//     co-operating on one patch at a time: EVAL (objective at the slot's current centre/normal), POST (stages
+//     after the refinement + result record + refill of the slot) and FILL (fetch a patch, stages before the
+//     refinement).  Their hot loop is small and stays resident in the instruction cache.
+// Slots hand over through a per-slot state word in shared memory; patches come from a global atomic counter.
 // ----------------------------------------------------------------------------------------------------------
-enum : int { SLOT_IDLE = 0, SLOT_NEW = 1, SLOT_ACTIVE = 2, SLOT_FINISHED = 3 };
+constexpr int QCAP = 1024;                // >= slots + sampler warps outstanding entries, power of two
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) optimize_kernel(const KParams K) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    WarpShared& WS = reinterpret_cast<WarpShared*>(smem_raw)[threadIdx.x >> 5];
-    Scratch& W = WS.S;
-    const int lane = threadIdx.x & 31;
-    LaneCtx& mine = WS.ctx[lane];
-    bq3::State bq;                       // this lane's optimiser (local memory)
-    double xcur[3] = {0.0, 0.0, 0.0};
-    double fcur = 0.0;
-    int slot = SLOT_IDLE;
-    bool queue_empty = false;
-    unsigned long long c_ok = 0, c_evals = 0, c_tex = 0, c_n = 0;
-    const unsigned lane_quota = (K.lanes_per_warp >= 32) ? FULL : ((1u << K.lanes_per_warp) - 1u);
+enum : int {
+    ST_EMPTY = 0,        // slot has no patch; a FILL request is (about to be) queued
+    ST_FILLING = 1,      // a sampler is fetching a patch / running the pre-stage
+    ST_NEW = 2,          // patch loaded, pre-stage passed: optimizer must start()
+    ST_EVAL_PENDING = 3, // objective requested
+    ST_EVAL_DONE = 4,    // objective value available in fval[slot]
+    ST_POSTING = 5,      // refinement finished, sampler runs the post-stage and retires the patch
+    ST_DEAD = 6          // no more work for this slot
+};
+enum : int { REQ_FILL = 1, REQ_EVAL = 2, REQ_POST = 3, REQ_EXIT = 4 };
 
-    for (;;) {
-        // ---- 1. refill idle lane slots: fetch a patch and run its pre-stage co-operatively -----------------
-        unsigned idle = __ballot_sync(FULL, slot == SLOT_IDLE) & lane_quota;
-        while (idle && !queue_empty) {
-            const int l = __ffs(idle) - 1;
-            int pi = 0;
-            if (lane == 0) pi = atomicAdd(K.work_counter, 1);
-            pi = __shfl_sync(FULL, pi, 0);
-            if (pi >= K.n) { queue_empty = true; break; }
-            LaneCtx& P = WS.ctx[l];
-            load_patch(P, K.in[pi], pi, lane);
-            const int st = pre_stage(W, P, K, lane);
-            if (st != HPMVS_OK) {
-                retire_patch(W, P, K, lane, st);
-                if (lane == 0) { c_n++; c_tex += P.textures; }
-                continue;                        // same slot, next patch
-            }
-            if (lane == l) slot = SLOT_NEW;
-            idle &= idle - 1;
-        }
-        // ---- 2. start the optimiser of freshly filled slots (lane-parallel) --------------------------------
-        if (slot == SLOT_NEW) {
-            const double lb[3] = {-HUGE_VAL, -23.99999, -23.99999};
-            const double ub[3] = {HUGE_VAL, 23.99999, 23.99999};
-            double x0[3];
-            init_parameters(mine, K, lb, ub, x0);
-            const int act = bq3::start(bq, x0, lb, ub, 1.e-7, 1000, xcur);
-            if (act == bq3::ASK) { set_center_norm(mine, K, xcur); slot = SLOT_ACTIVE; }
-            else slot = SLOT_FINISHED;
-        }
-        __syncwarp();
-        unsigned active = __ballot_sync(FULL, slot == SLOT_ACTIVE);
-        unsigned finished = __ballot_sync(FULL, slot == SLOT_FINISHED);
-        if (!active && !finished) break;         // nothing in flight and the queue is empty
-        // ---- 3. objective for every active slot, one after the other, all lanes co-operating ---------------
-        for (unsigned m = active; m; m &= m - 1) {
-            const int l = __ffs(m) - 1;
-            LaneCtx& P = WS.ctx[l];
-            eval_dots(W, P, K, lane, 0, false);
-            const double f = objective_value(W, P, K);
-            if (lane == l) fcur = f;
-            __syncwarp();
-        }
-        // ---- 4. advance every active optimiser (lane-parallel SIMT) ----------------------------------------
-        if (slot == SLOT_ACTIVE) {
-            const int act = bq3::advance(bq, fcur, xcur);
-            if (act == bq3::ASK) set_center_norm(mine, K, xcur);
-            else slot = SLOT_FINISHED;
-        }
-        if (slot == SLOT_FINISHED) {
-            // optimizePatch's epilogue (:364-381)
-            const int rc = bq.rc;
-            mine.nlopt_rc = rc; mine.evals = bq.nevals; mine.score = bq.minf;
-            if (rc >= 1 && rc <= 4) {
-                double xf[3];
-                bq3::result_x(bq, xf);
-                set_center_norm(mine, K, xf);
-                mine.status = HPMVS_OK;
-            } else {
-                mine.status = rc == bq3::R_ROUNDOFF_LIMITED ? HPMVS_FAIL_OPT_ROUNDOFF
-                              : rc == bq3::R_MAXEVAL_REACHED ? HPMVS_FAIL_OPT_MAXEVAL : HPMVS_FAIL_OPT_OTHER;
-            }
-        }
-        __syncwarp();
-        // ---- 5. retire finished slots: post-stage + colour + result record, co-operatively ------------------
-        finished = __ballot_sync(FULL, slot == SLOT_FINISHED);
-        for (unsigned m = finished; m; m &= m - 1) {
-            const int l = __ffs(m) - 1;
-            LaneCtx& P = WS.ctx[l];
-            int st = P.status;
-            if (st == HPMVS_OK) st = post_stage(W, P, K, lane);
-            retire_patch(W, P, K, lane, st);
-            if (lane == 0) { c_n++; c_ok += (st == HPMVS_OK); c_evals += P.evals; c_tex += P.textures; }
-            __syncwarp();
-        }
-        if (slot == SLOT_FINISHED) slot = SLOT_IDLE;
+struct QueueShared {
+    int queue[QCAP];
+    unsigned q_head, q_tail;
+    int opt_alive;
+    int pad;
+};
+
+// BOBYQA state of one slot, padded so that the 8-byte stride between lanes is odd (conflict-free 64-bit accesses
+// when all lanes of an optimizer warp touch the same field)
+struct __align__(8) BqSlot {
+    bq3::State s;
+    double pad[((sizeof(bq3::State) / 8) % 2 == 0) ? 1 : 2];
+};
+static_assert((sizeof(BqSlot) / 8) % 2 == 1, "BqSlot stride must be an odd number of 8-byte words");
+
+template <int OPT_WARPS, int SAMPLER_WARPS, int LPW>
+struct __align__(16) CtaSharedT {
+    static constexpr int NSLOTS = OPT_WARPS * LPW;   // LPW = lane slots used per optimizer warp (<= 32)
+    BqSlot bq[NSLOTS];
+    LaneCtx ctx[NSLOTS];
+    double fval[NSLOTS];
+    int sstate[NSLOTS];
+    QueueShared Q;
+    Scratch scratch[SAMPLER_WARPS];
+};
+
+__device__ __forceinline__ int ld_state(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+__device__ __forceinline__ void st_state(int* p, int v) {
+    __threadfence_block();
+    *reinterpret_cast<volatile int*>(p) = v;
+}
+__device__ __forceinline__ void q_push(QueueShared& C, int kind, int slot) {
+    const unsigned t = atomicAdd(&C.q_tail, 1u);
+    __threadfence_block();
+    *reinterpret_cast<volatile int*>(&C.queue[t & (QCAP - 1)]) = (kind << 16) | slot;
+}
+// whole warp: take the next ticket and wait for its entry
+__device__ __forceinline__ int q_pop(QueueShared& C, int lane) {
+    int e = 0;
+    if (lane == 0) {
+        const unsigned h = atomicAdd(&C.q_head, 1u);
+        volatile int* q = &C.queue[h & (QCAP - 1)];
+        while ((e = *q) == 0) __nanosleep(64);
+        *q = 0;
+        __threadfence_block();
     }
-    if (lane == 0 && c_n) {
-        atomicAdd(&K.counters[0], c_n); atomicAdd(&K.counters[1], c_ok);
-        atomicAdd(&K.counters[2], c_evals); atomicAdd(&K.counters[3], c_tex);
+    return __shfl_sync(FULL, e, 0);
+}
+
+// FILL: fetch patches until one passes the pre-stage (-> ST_NEW) or the queue is empty (-> ST_DEAD)
+__device__ __noinline__ void serve_fill(LaneCtx& P, int* sstate_slot, Scratch& W, const KParams& K, int lane, unsigned long long* cnt) {
+    for (;;) {
+        int pi = 0;
+        if (lane == 0) pi = atomicAdd(K.work_counter, 1);
+        pi = __shfl_sync(FULL, pi, 0);
+        if (pi >= K.n) {
+            if (lane == 0) st_state(sstate_slot, ST_DEAD);
+            return;
+        }
+        load_patch(P, K.in[pi], pi, lane);
+        const int st = pre_stage(W, P, K, lane);
+        if (st == HPMVS_OK) {
+            __syncwarp();
+            if (lane == 0) st_state(sstate_slot, ST_NEW);
+            return;
+        }
+        retire_patch(W, P, K, lane, st);
+        if (lane == 0) { cnt[0]++; cnt[3] += P.textures; }
+    }
+}
+
+template <int OPT_WARPS, int SAMPLER_WARPS, int LPW>
+__global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_kernel(const KParams K) {
+    using CtaShared = CtaSharedT<OPT_WARPS, SAMPLER_WARPS, LPW>;
+    constexpr int NSLOTS = CtaShared::NSLOTS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CtaShared& C = *reinterpret_cast<CtaShared*>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+
+    // ---- CTA set-up ------------------------------------------------------------------------------------------
+    for (int i = threadIdx.x; i < QCAP; i += blockDim.x) C.Q.queue[i] = 0;
+    for (int i = threadIdx.x; i < NSLOTS; i += blockDim.x) C.sstate[i] = ST_EMPTY;
+    if (threadIdx.x == 0) { C.Q.q_head = 0; C.Q.q_tail = 0; C.Q.opt_alive = OPT_WARPS; }
+    __syncthreads();
+
+    if (warp < OPT_WARPS) {
+        // =========================================== optimizer warp ===========================================
+        const bool has_slot = lane < LPW;
+        const int slot = warp * LPW + (has_slot ? lane : 0);     // lanes without a slot alias slot 0 but never touch it
+        LaneCtx& mine = C.ctx[slot];
+        int* my_state = &C.sstate[slot];
+        bq3::State& bq = C.bq[slot].s;   // shared memory: guaranteed on-chip (local memory thrashed L1, see profiles/)
+        double xcur[3] = {0.0, 0.0, 0.0};
+        // slots beyond the per-warp quota never receive work (small batches are spread over all SMs instead)
+        if (has_slot) {
+            if (lane < K.lanes_per_warp) { st_state(my_state, ST_FILLING); q_push(C.Q, REQ_FILL, slot); }
+            else st_state(my_state, ST_DEAD);
+        }
+        long long t_wait = 0, t_adv = 0, n_rounds = 0, n_lanes = 0;
+        for (;;) {
+            // wait until every requested objective of this warp has arrived and at least one lane can move
+            int st;
+            const long long tw0 = HP_CLOCK();
+            for (;;) {
+                st = has_slot ? ld_state(my_state) : ST_DEAD;
+                const unsigned waiting = __ballot_sync(FULL, st == ST_EVAL_PENDING);
+                const unsigned ready = __ballot_sync(FULL, st == ST_EVAL_DONE || st == ST_NEW);
+                const unsigned dead = __ballot_sync(FULL, st == ST_DEAD);
+                if (dead == FULL) { st = -1; break; }
+                if (!waiting && ready) break;
+                __nanosleep(200);
+            }
+            if (st == -1) break;
+            __threadfence_block();
+            const long long ta0 = HP_CLOCK();
+            t_wait += ta0 - tw0; n_rounds++; n_lanes += __popc(__ballot_sync(FULL, st == ST_EVAL_DONE || st == ST_NEW));
+            if (st == ST_NEW) {
+                const double lb[3] = {-HUGE_VAL, -23.99999, -23.99999};
+                const double ub[3] = {HUGE_VAL, 23.99999, 23.99999};
+                double x0[3];
+                init_parameters(mine, K, lb, ub, x0);
+                const int act = bq3::start(bq, x0, lb, ub, 1.e-7, 1000, xcur);
+                if (act == bq3::ASK) { set_center_norm(mine, K, xcur); st = ST_EVAL_PENDING; }
+                else st = ST_POSTING;
+            } else if (st == ST_EVAL_DONE) {
+                const double f = *reinterpret_cast<volatile double*>(&C.fval[slot]);
+                const int act = bq3::advance(bq, f, xcur);
+                if (act == bq3::ASK) { set_center_norm(mine, K, xcur); st = ST_EVAL_PENDING; }
+                else st = ST_POSTING;
+            } else {
+                st = 0;   // FILLING / POSTING / DEAD: nothing to do for this lane in this round
+            }
+            if (st == ST_POSTING) {
+                // optimizePatch's epilogue (:364-381)
+                const int rc = bq.rc;
+                mine.nlopt_rc = rc; mine.evals = bq.nevals; mine.score = bq.minf;
+                if (rc >= 1 && rc <= 4) {
+                    double xf[3];
+                    bq3::result_x(bq, xf);
+                    set_center_norm(mine, K, xf);
+                    mine.status = HPMVS_OK;
+                } else {
+                    mine.status = rc == bq3::R_ROUNDOFF_LIMITED ? HPMVS_FAIL_OPT_ROUNDOFF
+                                  : rc == bq3::R_MAXEVAL_REACHED ? HPMVS_FAIL_OPT_MAXEVAL : HPMVS_FAIL_OPT_OTHER;
+                }
+            }
+            if (st == ST_EVAL_PENDING) { st_state(my_state, ST_EVAL_PENDING); q_push(C.Q, REQ_EVAL, slot); }
+            else if (st == ST_POSTING) { st_state(my_state, ST_POSTING); q_push(C.Q, REQ_POST, slot); }
+            __syncwarp();
+            t_adv += HP_CLOCK() - ta0;
+        }
+#ifdef HP_PROFILE
+        if (lane == 0) {
+            atomicAdd(&K.counters[4], (unsigned long long)t_wait); atomicAdd(&K.counters[5], (unsigned long long)t_adv);
+            atomicAdd(&K.counters[6], (unsigned long long)n_rounds); atomicAdd(&K.counters[7], (unsigned long long)n_lanes);
+        }
+#endif
+        // the last optimizer warp to finish releases the samplers
+        __syncwarp();
+        if (lane == 0) {
+            if (atomicSub(&C.Q.opt_alive, 1) == 1)
+                for (int i = 0; i < SAMPLER_WARPS; i++) q_push(C.Q, REQ_EXIT, 0);
+        }
+    } else {
+        // ============================================ sampler warp ============================================
+        Scratch& W = C.scratch[warp - OPT_WARPS];
+        unsigned long long cnt[4] = {0, 0, 0, 0};   // patches, ok, evals, textures (lane 0 only)
+        long long t_idle = 0, t_eval = 0, t_other = 0, n_eval = 0;
+        for (;;) {
+            const long long tq0 = HP_CLOCK();
+            const int e = q_pop(C.Q, lane);
+            const long long tq1 = HP_CLOCK();
+            t_idle += tq1 - tq0;
+            const int kind = e >> 16, slot = e & 0xffff;
+            if (kind == REQ_EXIT) break;
+            LaneCtx& P = C.ctx[slot];
+            if (kind == REQ_EVAL) {
+                eval_dots(W, P, K, lane, 0, false);
+                const double f = objective_value(W, P, K);
+                __syncwarp();
+                if (lane == 0) {
+                    *reinterpret_cast<volatile double*>(&C.fval[slot]) = f;
+                    st_state(&C.sstate[slot], ST_EVAL_DONE);
+                }
+                t_eval += HP_CLOCK() - tq1; n_eval++;
+            } else if (kind == REQ_POST) {
+                int st = P.status;
+                if (st == HPMVS_OK) st = post_stage(W, P, K, lane);
+                retire_patch(W, P, K, lane, st);
+                if (lane == 0) { cnt[0]++; cnt[1] += (st == HPMVS_OK); cnt[2] += P.evals; cnt[3] += P.textures; }
+                __syncwarp();
+                serve_fill(P, &C.sstate[slot], W, K, lane, cnt);
+            } else {   // REQ_FILL
+                serve_fill(P, &C.sstate[slot], W, K, lane, cnt);
+            }
+            __syncwarp();
+        }
+        if (lane == 0 && cnt[0]) {
+            atomicAdd(&K.counters[0], cnt[0]); atomicAdd(&K.counters[1], cnt[1]);
+            atomicAdd(&K.counters[2], cnt[2]); atomicAdd(&K.counters[3], cnt[3]);
+        }
+#ifdef HP_PROFILE
+        if (lane == 0) {
+            atomicAdd(&K.counters[8], (unsigned long long)t_idle); atomicAdd(&K.counters[9], (unsigned long long)t_eval);
+            atomicAdd(&K.counters[10], (unsigned long long)n_eval);
+        }
+#endif
+        (void)t_other;
     }
 }
 

@@ -7,9 +7,13 @@ ia, isamp, iexec, inoinst, ilong, iwait = [hdr.index(x) for x in ("Address", "# 
 isrc = hdr.index("Source")
 # symbol ranges from the ELF (offsets inside the kernel's .text)
 elf = subprocess.run(["cuobjdump", "-elf", sys.argv[2]], capture_output=True, text=True).stdout
+kname = sys.argv[3] if len(sys.argv) > 3 else "optimize_kernelILi2ELi10ELi32"
+shndx = None
+for m in re.finditer(r"^\s*0x[0-9a-f]+\s+(?:0x[0-9a-f]+|0)\s+(?:0x[0-9a-f]+|0)\s+0x12\s+\S+\s+(0x[0-9a-f]+)\s+(\S+)", elf, re.M):
+    if kname in m.group(2): shndx = m.group(1)
 syms = []
-for m in re.finditer(r"^\s*0x[0-9a-f]+\s+(0x[0-9a-f]+|0)\s+(0x[0-9a-f]+)\s+0x(?:2|22)\s+\S+\s+0x1e\s+(\S+)", elf, re.M):
-    syms.append((int(m.group(1), 16), int(m.group(2), 16), m.group(3)))
+for m in re.finditer(r"^\s*0x[0-9a-f]+\s+(0x[0-9a-f]+|0)\s+(0x[0-9a-f]+)\s+0x(?:2|22)\s+\S+\s+(0x[0-9a-f]+)\s+(\S+)", elf, re.M):
+    if m.group(3) == shndx: syms.append((int(m.group(1), 16), int(m.group(2), 16), m.group(4)))
 syms.sort()
 base = None
 agg = collections.defaultdict(lambda: [0, 0, 0, 0, 0])

@@ -1,0 +1,118 @@
+"""Sanity and known-answer checks of the CPU oracle itself (test infrastructure) - no GPU.
+
+HPMVS ships no golden vectors, so the oracle is pinned where something external exists:
+  * the optimiser = the reference's own BOBYQA object code, checked on nlopt's Box-Betts known answer (test_bobyqa.py);
+  * Q16 of the survey's quirk ledger: with 2 views and default options nothing survives (known answer "0 patches");
+  * analytic properties of the photometric pieces (NCC of a texture with itself = 1, pyramid of a constant image, ...);
+  * the committed golden fixture tests/golden/plane4_small.npz (minted by tests/golden/make_golden.py from this
+    oracle: a regression pin, not an external one)."""
+import os
+
+import numpy as np
+import pytest
+
+import hpmvs_b200 as hp
+import oracle
+from helpers import small_plane
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_two_views_default_options_yield_zero_patches():
+    # BASELINE config 1: 2 cameras 640x480 f=600 at x=+-1, z=-6; 16 seeds on a 4x4 grid; MIN_IMAGES_PER_PATCH = 3
+    sc = hp.synth.plane_scene(n_views=2, width=640, height=480, focal=600.0, radius=6.08, arc_deg=18.9, n_seeds=16,
+                              extent=0.5, seed=1, tex_size=256, depth_noise=0.0)
+    orc = oracle.OracleScene.from_synth(sc)
+    seeds, valid = orc.seed_patches(sc.points, sc.meas_offsets, sc.meas_cam)
+    assert valid.sum() == 0          # Scene.cpp:128: fewer than MIN_IMAGES_PER_PATCH measurements
+    # explicit override MIN_IMAGES_PER_PATCH=2 makes the plumbing produce patches
+    orc2 = oracle.OracleScene.from_synth(sc, oracle.Options.defaults(min_images_per_patch=2))
+    orc2.set_covis([[1], [0]])
+    seeds2, valid2 = orc2.seed_patches(sc.points, sc.meas_offsets, sc.meas_cam)
+    assert valid2.sum() == 16
+    out = orc2.optimize_batch(seeds2[valid2])
+    assert (out["status"] == 0).sum() >= 8
+    ok = out["status"] == 0
+    assert np.abs(out["center"][ok][:, 2]).max() < 0.15          # refined onto the plane z = 0
+    assert (np.abs(out["normal"][ok][:, 2]) > 0.97).all()
+
+
+def test_pyramid_properties():
+    img = np.full((37, 50, 3), 200, np.uint8)
+    img[:, :, 1] = 77
+    orc = oracle.OracleScene()
+    orc.add_camera(100.0, [1, 0, 0, 0], [0, 0, 0], img)
+    w, h = 50, 37
+    for lvl in range(1, 6):
+        w, h = w // 2, h // 2
+        p = orc.image(0, lvl)
+        assert p.shape == (h, w, 3)
+        # constant image: mask sums to ~1, truncation may lose at most one grey level per octave (Q14)
+        assert np.all(p[..., 0] <= 200) and np.all(p[..., 0] >= 200 - lvl)
+        assert np.all(p[..., 1] <= 77) and np.all(p[..., 1] >= 77 - lvl)
+
+
+def test_ncc_of_reference_with_itself_and_robust_function():
+    sc, orc, seeds = small_plane()
+    k = next(i for i in range(len(seeds)) if orc.set_inccs(seeds[i:i + 1], 0, 0)[0] == 0.0)   # reference view samples fine
+    p = seeds[k:k + 1].copy()
+    p["images"][0, 1] = p["images"][0, 0]        # the same view twice => identical textures
+    inc = orc.set_inccs(p, 0, 0)
+    assert inc[0] == 0.0 and abs(inc[1]) < 1e-6  # 1 - NCC(t, t) = 0
+    r = orc.set_inccs(seeds[k:k + 1], 0, 0)
+    rr = orc.set_inccs(seeds[k:k + 1], 0, 1)
+    v = r < 2.0
+    assert np.allclose(rr[v], r[v] / (1 + 3 * r[v]), atol=1e-6)   # robustincc, PatchOptimizer.h:92-94
+
+
+def test_sample_texture_is_normalised():
+    sc, orc, seeds = small_plane()
+    done = 0
+    for p in seeds[::7]:
+        cam = int(p["images"][0])
+        # any in-plane axes of length scale will do for this property
+        x = np.array([p["scale"], 0, 0, 0], np.float32); y = np.array([0, p["scale"], 0, 0], np.float32)
+        ok, tex = orc.sample_texture(p["center"], p["scale"], x, y, p["normal"], cam)
+        if not ok:
+            continue
+        t = tex.reshape(49, 3)
+        assert np.abs(t.mean(0)).max() < 1e-4 and abs((t ** 2).mean() - 1.0) < 1e-4   # Patch2d.hpp:46-84
+        done += 1
+    assert done > 5
+
+
+def test_covisibility_bug_compat():
+    # 60 points, each measured in cameras (5, 7, 9): the reference counts POSITIONS 0,1,2 (Scene.cpp:260-264)
+    offs = np.arange(0, 61 * 3, 3, dtype=np.int32)
+    cams = np.tile(np.array([5, 7, 9], np.int32), 60)
+    compat = hp.extract_covis(12, offs, cams, compat=True)
+    fixed = hp.extract_covis(12, offs, cams, compat=False)
+    assert compat[0] == [1, 2] and compat[1] == [0, 2] and compat[2] == [0, 1] and compat[5] == []
+    assert fixed[5] == [7, 9] and fixed[7] == [5, 9] and fixed[0] == []
+
+
+def test_optimize_converges_on_plane():
+    sc, orc, seeds = small_plane()
+    out = orc.optimize_batch(seeds, nthreads=4)
+    ok = out["status"] == 0
+    assert ok.sum() > 0.5 * len(seeds)
+    assert np.abs(out["center"][ok][:, 2]).mean() < np.abs(seeds["center"][ok][:, 2]).mean()
+    assert (out["normal"][ok][:, 2] < -0.8).mean() > 0.9           # plane normal faces the cameras (-z)
+    assert (out["ncc"][ok] == np.float32(1.4)).all()                # Q5
+    assert out["evals"][ok].min() >= 7 and out["evals"].max() <= 1000
+
+
+def test_golden_fixture():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "plane4_small.npz"))
+    sc = hp.synth.plane_scene(**{k: (v.item() if hasattr(v, "item") else v) for k, v in eval(str(g["scene_kwargs"])).items()})
+    import hashlib
+    assert hashlib.sha256(np.stack(sc.images).tobytes()).hexdigest() == str(g["scene_sha256"]), "synthetic scene generator changed: regenerate the golden fixture"
+    orc = oracle.OracleScene.from_synth(sc)
+    seeds, valid = orc.seed_patches(sc.points, sc.meas_offsets, sc.meas_cam)
+    oracle.set_cr_asinf(True)
+    try:
+        out = orc.optimize_batch(seeds[valid], nthreads=2)
+    finally:
+        oracle.set_cr_asinf(False)
+    for f in ("status", "center", "normal", "nimages", "images", "color", "evals"):
+        assert np.array_equal(out[f], g[f]), f
