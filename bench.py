@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="plane8", choices=["plane8", "city100", "tiny"])
+    ap.add_argument("--workload", default="plane8", choices=["plane8", "plane8x100k", "city100", "tiny"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="patches in the cpu_baseline sample (0 = auto)")
     return ap.parse_args()
 
@@ -50,10 +50,14 @@ def workload_scene(name: str, rank: int = 0):
     from hpmvs_b200 import synth
     if name == "plane8":
         return synth.plane_scene(n_views=8, width=1280, height=960, focal=1200.0, radius=8.0, arc_deg=40.0,
-                                 n_seeds=10000, extent=2.5, seed=2 + 1000 * rank, tex_size=1024), \
+                                 n_seeds=10000, extent=2.5, seed=2, point_seed=2 + 1000 * rank, tex_size=1024), \
             "8-view 1280x960 synthetic plane, 10k seed patches (BASELINE.json configs[1])"
+    if name == "plane8x100k":
+        return synth.plane_scene(n_views=8, width=1280, height=960, focal=1200.0, radius=8.0, arc_deg=40.0,
+                                 n_seeds=100000, extent=2.5, seed=2, point_seed=2 + 1000 * rank, tex_size=1024), \
+            "8-view 1280x960 synthetic plane, 100k seed patches (configs[1] scene, 10x the seeds: steady-state throughput)"
     if name == "tiny":
-        return synth.plane_scene(n_views=8, width=640, height=480, focal=600.0, n_seeds=2000, seed=2 + 1000 * rank,
+        return synth.plane_scene(n_views=8, width=640, height=480, focal=600.0, n_seeds=2000, seed=2, point_seed=2 + 1000 * rank,
                                  tex_size=512), "8-view 640x480 synthetic plane, 2k seed patches (smoke size)"
     return synth.city_scene(n_views=100, width=1920, height=1080, n_seeds=100000, seed=4 + 1000 * rank), \
         "100-view 1080p synthetic city block, 100k seed patches (BASELINE.json configs[3] on 1 GPU)"
@@ -286,6 +290,18 @@ def main():
     out_np = h_out.numpy().view(hp.PATCH_DTYPE).reshape(n)
     ok_e2e = int((out_np["status"] == 0).sum())
 
+    # ---- final exchange (untimed for `value`): variable-length NCCL gather of the patch records + border de-dup ----
+    gather_ms, merged = None, None
+    if dist is not None:
+        from hpmvs_b200 import gather
+        torch.cuda.synchronize(); dist.barrier()
+        tg = time.perf_counter()
+        allr, owner = gather.gather_patches(out_np[out_np["status"] == 0])
+        keep = gather.dedup_border(allr, owner, cell=float(np.median(out_np["scale"])))
+        torch.cuda.synchronize()
+        gather_ms = 1e3 * (time.perf_counter() - tg)
+        merged = (int(len(allr)), int(len(keep)))
+
     # ---- reduce over ranks -------------------------------------------------------------------------------------
     stats = torch.tensor([t_dev, t_e2e, ok_per_step, tex_per_step, float(n), evals_per_step, float(ok_e2e)], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -325,7 +341,8 @@ def main():
                 "config": {"workload": desc, "patches_per_step_per_gpu": int(n), "optimized_per_step": ok_all,
                            "evals_per_step": evals_all, "textures_per_step": tex_all, "l2": "flushed between steps (256 MiB write)",
                            "parallelism": f"patch shards x{world}, scene replicated, no data-path collective",
-                           "wall_s_timed_region": t_wall},
+                           "wall_s_timed_region": t_wall, "final_gather_dedup_ms": gather_ms,
+                           "patches_gathered_kept": merged},
                 "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": "patches/s", "h2d_bytes_per_step": int(n * REC_BYTES), "d2h_bytes_per_step": int(n * REC_BYTES),
                         "ms_per_step": 1e3 * t_e2e_max / args.steps},

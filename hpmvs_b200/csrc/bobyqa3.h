@@ -31,6 +31,10 @@
 // SM's instruction cache.
 #if defined(__CUDA_ARCH__)
 #define BQ_NOUNROLL _Pragma("unroll 1")
+#ifdef BQ_ALLOW_UNROLL
+#undef BQ_NOUNROLL
+#define BQ_NOUNROLL
+#endif
 #else
 #define BQ_NOUNROLL
 #endif
@@ -53,6 +57,14 @@
 #define BQ_SCHED_BEGIN(mask, done, key) \
     if (done) break;
 #define BQ_ACTIVE_MASK() 0xffffffffu
+#endif
+
+// The engine keeps every State in shared memory; telling the compiler lets it emit LDS/STS with immediate offsets
+// instead of generic loads plus address arithmetic.
+#if defined(__CUDA_ARCH__) && defined(BQ_STATE_IN_SHARED)
+#define BQ_ASSUME_SHARED(S) __builtin_assume(__isShared(&(S)))
+#else
+#define BQ_ASSUME_SHARED(S)
 #endif
 
 namespace bq3 {
@@ -122,6 +134,7 @@ BQ_HD double default_step(double lb, double ub, double x) {
 // H-matrix update when interpolation point `knew` moves (Powell's UPDATE)
 // ---------------------------------------------------------------------------------------------------------
 BQ_HDN void update(State& S, double beta, double denom, int knew, double* w) {
+    BQ_ASSUME_SHARED(S);
     double (*zmat)[NPTM] = S.zmat;
     double (*bmat)[N] = S.bmat;
     double* vlag = S.vlag;
@@ -171,6 +184,7 @@ BQ_HDN void update(State& S, double beta, double denom, int knew, double* w) {
 // glag = w[0..2], hcol = w[3..9], wa = w[10..15]
 // ---------------------------------------------------------------------------------------------------------
 BQ_HDN void altmov(State& S) {
+    BQ_ASSUME_SHARED(S);
     double (*xpt)[N] = S.xpt;
     double (*zmat)[NPTM] = S.zmat;
     double (*bmat)[N] = S.bmat;
@@ -329,6 +343,7 @@ BQ_HDN void altmov(State& S) {
 // boundary (two-dimensional) refinements.  gnew=w[0..2] xbdi=w[3..5] s=w[6..8] hs=w[9..11] hred=w[12..14]
 // ---------------------------------------------------------------------------------------------------------
 BQ_HD void hess_mul(const State& S, const double* s, double* hs) {
+    BQ_ASSUME_SHARED(S);
     int ih = 0;
     BQ_NOUNROLL for (int j = 0; j < N; j++) {
         hs[j] = 0.0;
@@ -349,6 +364,7 @@ BQ_HD void hess_mul(const State& S, const double* s, double* hs) {
 }
 
 BQ_HDN void trsbox(State& S, unsigned wmask) {
+    BQ_ASSUME_SHARED(S);
     double* xopt = S.xopt; double* gopt = S.gopt; double* sl = S.sl; double* su = S.su;
     double* xnew = S.xnew; double* d = S.d;
     double* gnew = S.w; double* xbdi = S.w + 3; double* s = S.w + 6; double* hs = S.w + 9; double* hred = S.w + 12;
@@ -575,6 +591,7 @@ BQ_HDN void trsbox(State& S, unsigned wmask) {
 
 // point handed to the objective: x = clamp(xbase + p) with exact bounds where p sits on sl/su
 BQ_HD void point_from(State& S, const double* p) {
+    BQ_ASSUME_SHARED(S);
     BQ_NOUNROLL for (int i = 0; i < N; i++) {
         S.x[i] = dmin(dmax(S.xl[i], S.xbase[i] + p[i]), S.xu[i]);
         if (p[i] == S.sl[i]) S.x[i] = S.xl[i];
@@ -587,6 +604,7 @@ BQ_HD void point_from(State& S, const double* p) {
 // ptsaux = w[0..5] (ptsaux[j][0|1] -> w[2j], w[2j+1]), ptsid = w[6..12], scratch wr = w[13..29]
 // ---------------------------------------------------------------------------------------------------------
 BQ_HDN void rescue_setup(State& S) {
+    BQ_ASSUME_SHARED(S);
     double (*xpt)[N] = S.xpt; double (*bmat)[N] = S.bmat; double (*zmat)[NPTM] = S.zmat;
     double* xopt = S.xopt; double* sl = S.sl; double* su = S.su; double* hq = S.hq; double* pq = S.pq;
     double* vlag = S.vlag;
@@ -730,6 +748,7 @@ BQ_HDN void rescue_setup(State& S) {
 
 // RESCUE, part 2a: place provisional point kpt, predict the model there, emit the point to evaluate.
 BQ_HDN void rescue_place(State& S, int kpt) {
+    BQ_ASSUME_SHARED(S);
     double (*xpt)[N] = S.xpt;
     double* hq = S.hq; double* pq = S.pq; double* gopt = S.gopt;
     double* ptsaux = S.w; double* ptsid = S.w + 6; double* wr = S.w + 13;
@@ -778,6 +797,7 @@ BQ_HDN void rescue_place(State& S, int kpt) {
 
 // RESCUE, part 2b: absorb f at provisional point kpt into the model.
 BQ_HDN void rescue_absorb(State& S, int kpt, double f) {
+    BQ_ASSUME_SHARED(S);
     double (*bmat)[N] = S.bmat; double (*zmat)[NPTM] = S.zmat;
     double* hq = S.hq; double* pq = S.pq; double* gopt = S.gopt;
     double* ptsaux = S.w; double* ptsid = S.w + 6;
@@ -820,6 +840,7 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out);
 
 BQ_HDN int start(State& S, const double* x0, const double* lb, const double* ub, double xtol_rel, int maxeval,
                  double* xs_out) {
+    BQ_ASSUME_SHARED(S);
     S.maxeval = maxeval;
     S.nevals = 0;
     S.rc = R_SUCCESS;
@@ -886,6 +907,7 @@ BQ_HD void result_x(const State& S, double* xs_out) {
 }
 
 BQ_HDN int advance(State& S, double f_in, double* xs_out) {
+    BQ_ASSUME_SHARED(S);
     double (*xpt)[N] = S.xpt; double (*bmat)[N] = S.bmat; double (*zmat)[NPTM] = S.zmat;
     double* xopt = S.xopt; double* gopt = S.gopt; double* hq = S.hq; double* pq = S.pq; double* fval = S.fval;
     double* sl = S.sl; double* su = S.su; double* xnew = S.xnew; double* xalt = S.xalt; double* d = S.d;

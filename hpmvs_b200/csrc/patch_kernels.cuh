@@ -23,6 +23,7 @@
 #include <stdint.h>
 
 #include "../../include/hpmvs_b200.h"
+#define BQ_STATE_IN_SHARED 1
 #include "bobyqa3.h"
 
 namespace hp {

@@ -1,0 +1,63 @@
+"""Final multi-GPU exchange of the patch-optimisation path: variable-length gather of patch records over
+torch.distributed (NCCL on GPUs, gloo in the CPU tests) and border de-duplication.
+
+The reference is one process with shared memory; its analogue of cross-shard traffic is the border hand-off
+between sub-trees (/root/reference/src/hpmvs/CellProcessor.cpp:487-540).  Here every rank optimises its own shard of
+sub-trees and only the final patch sets are exchanged: all_gather of the counts, then one padded all_gather of the
+208-byte records.  Patches from different ranks that fall into the same finest-level cell are then reduced to the
+best-supported one, the rule of CellProcessor::filter (src/hpmvs/CellProcessor.cpp:43-82: most views wins).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .engine import PATCH_DTYPE
+
+REC = PATCH_DTYPE.itemsize
+
+
+def gather_patches(records: np.ndarray, device: Optional[torch.device] = None) -> Tuple[np.ndarray, np.ndarray]:
+    """All ranks receive the concatenation of every rank's records (rank order) and the owning rank of each."""
+    assert records.dtype == PATCH_DTYPE
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return records.copy(), np.zeros(len(records), np.int32)
+    world = dist.get_world_size()
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    n = torch.tensor([len(records)], dtype=torch.int64, device=device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1)
+    buf = torch.zeros((cap, REC), dtype=torch.uint8, device=device)
+    if len(records):
+        buf[:len(records)] = torch.from_numpy(np.ascontiguousarray(records).view(np.uint8).reshape(len(records), REC)).to(device)
+    out = torch.empty((world, cap, REC), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(out.view(world * cap, REC), buf)
+    host = out.cpu().numpy()
+    parts = [host[r, :counts[r]].reshape(-1).view(PATCH_DTYPE) for r in range(world)]
+    owner = np.concatenate([np.full(counts[r], r, np.int32) for r in range(world)]) if sum(counts) else np.zeros(0, np.int32)
+    return np.concatenate(parts) if sum(counts) else np.zeros(0, PATCH_DTYPE), owner
+
+
+def dedup_border(records: np.ndarray, owner: np.ndarray, cell: float) -> np.ndarray:
+    """Keep one patch per cubic cell of edge `cell` when ranks disagree: most views first (CellProcessor::filter),
+    then the lower final score, then the lower rank.  Patches of a single rank are never merged (that is the
+    host scheduler's job inside a sub-tree).  Returns the indices kept, ascending."""
+    ok = records["status"] == 0
+    idx = np.nonzero(ok)[0]
+    if len(idx) == 0:
+        return idx
+    key = np.floor(records["center"][idx, :3].astype(np.float64) / cell).astype(np.int64)
+    order = np.lexsort((owner[idx], records["score"][idx], -records["nimages"][idx], key[:, 2], key[:, 1], key[:, 0]))
+    k = key[order]
+    first = np.ones(len(order), bool)
+    first[1:] = (k[1:] != k[:-1]).any(1)
+    cell_id = np.cumsum(first) - 1
+    winner_owner = owner[idx][order][first][cell_id]
+    keep = first | (owner[idx][order] == winner_owner)       # same-rank neighbours of the winner stay
+    return np.sort(idx[order][keep])

@@ -185,12 +185,12 @@ def _visible(cam: NVMCamera, X: np.ndarray, margin: float) -> np.ndarray:
 def plane_scene(n_views: int = 8, width: int = 1280, height: int = 960, focal: float = 1200.0,
                 radius: float = 8.0, arc_deg: float = 40.0, n_seeds: int = 10000, extent: float = 2.5,
                 seed: int = 2, tex_size: int = 1024, depth_noise: float = 0.5, plane_half: float = 6.0,
-                name: Optional[str] = None, elev_deg: float = 6.0) -> SynthScene:
+                name: Optional[str] = None, elev_deg: float = 6.0, point_seed: Optional[int] = None) -> SynthScene:
     """BASELINE config 2 family: cameras on an arc of `arc_deg` at distance `radius` around a textured
     plane z=0.  Seeds: jittered sqrt(n) x sqrt(n) grid over +-extent, displaced along the plane
     normal by N(0,(depth_noise*scale)^2) with scale = 16*radius/focal (getScale at START_LEVEL 4).
     Every seed is measured in every view that sees it."""
-    rng = np.random.Generator(np.random.PCG64(seed))
+    rng = np.random.Generator(np.random.PCG64(seed if point_seed is None else point_seed))   # seed points only
     tex = noise_texture(tex_size, seed * 7919 + 1)
     quad = Quad(np.array([-plane_half, -plane_half, 0.0]), np.array([2 * plane_half, 0, 0.0]),
                 np.array([0, 2 * plane_half, 0.0]), tex)

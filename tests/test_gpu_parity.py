@@ -102,7 +102,8 @@ def test_golden_fixture(plane):
     assert np.array_equal(got["status"], g["status"])
     for f in ("center", "normal", "nimages", "color", "evals"):
         assert np.array_equal(got[f][ok], g[f][ok]), f
-    assert np.array_equal(got["images"][ok], g["images"][ok][:, :hp.MAX_VIEWS])
+    for a, b, n in zip(got["images"][ok], g["images"][ok], g["nimages"][ok]):
+        assert np.array_equal(a[:n], b[:n])          # entries past nimages are unspecified
     assert np.array_equal(got["score"][ok], g["last_val"][ok])
 
 
