@@ -31,12 +31,12 @@
 // SM's instruction cache.
 #if defined(__CUDA_ARCH__)
 #define BQ_NOUNROLL _Pragma("unroll 1")
-#ifdef BQ_ALLOW_UNROLL
-#undef BQ_NOUNROLL
-#define BQ_NOUNROLL
-#endif
+// innermost 3-trip loops with one-statement bodies (and hess_mul) ARE unrolled: the per-label cycle profile
+// (profiles/) showed the rolled multiply-accumulate loops costing ~10 instructions per MAC.
+#define BQ_UNROLL _Pragma("unroll")
 #else
 #define BQ_NOUNROLL
+#define BQ_UNROLL
 #endif
 
 // Warp-converged dispatch of the label state machines below (device only).  Lanes of one warp run different
@@ -68,6 +68,12 @@
 #endif
 
 namespace bq3 {
+
+#if defined(__CUDACC__) && defined(HP_PROFILE)
+__device__ unsigned long long g_prof_cycles[16];
+__device__ unsigned long long g_prof_trips[16];
+__device__ unsigned long long g_prof_lanes[16];
+#endif
 
 enum : int { N = 3, NPT = 7, NDIM = 10, NPTM = 3, NP = 4, NH = 6 };
 
@@ -140,7 +146,7 @@ BQ_HDN void update(State& S, double beta, double denom, int knew, double* w) {
     double* vlag = S.vlag;
     double ztest = 0.0;
     BQ_NOUNROLL for (int k = 0; k < NPT; k++)
-        BQ_NOUNROLL for (int j = 0; j < NPTM; j++) ztest = dmax(ztest, fabs(zmat[k][j]));
+        BQ_UNROLL for (int j = 0; j < NPTM; j++) ztest = dmax(ztest, fabs(zmat[k][j]));
     ztest *= 1e-20;
     // rotations that zero the knew-th row of zmat beyond its first column
     BQ_NOUNROLL for (int j = 1; j < NPTM; j++) {
@@ -200,12 +206,12 @@ BQ_HDN void altmov(State& S) {
     }
     S.alpha = hcol[knew];
     const double ha = 0.5 * S.alpha;
-    BQ_NOUNROLL for (int i = 0; i < N; i++) glag[i] = bmat[knew][i];
+    BQ_UNROLL for (int i = 0; i < N; i++) glag[i] = bmat[knew][i];
     BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
         double temp = 0.0;
-        BQ_NOUNROLL for (int j = 0; j < N; j++) temp += xpt[k][j] * xopt[j];
+        BQ_UNROLL for (int j = 0; j < N; j++) temp += xpt[k][j] * xopt[j];
         temp = hcol[k] * temp;
-        BQ_NOUNROLL for (int i = 0; i < N; i++) glag[i] += temp * xpt[k][i];
+        BQ_UNROLL for (int i = 0; i < N; i++) glag[i] += temp * xpt[k][i];
     }
     // search along lines through xopt and the other points
     double presav = 0.0, stpsav = 0.0;
@@ -311,7 +317,7 @@ BQ_HDN void altmov(State& S) {
         double curv = 0.0;
         BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
             double temp = 0.0;
-            BQ_NOUNROLL for (int j = 0; j < N; j++) temp += xpt[k][j] * wa[j];
+            BQ_UNROLL for (int j = 0; j < N; j++) temp += xpt[k][j] * wa[j];
             curv += hcol[k] * temp * temp;
         }
         if (iflag == 1) curv = -curv;
@@ -328,12 +334,12 @@ BQ_HDN void altmov(State& S) {
             S.cauchy = t * t;
         }
         if (iflag == 0) {
-            BQ_NOUNROLL for (int i = 0; i < N; i++) { glag[i] = -glag[i]; wa[N + i] = xalt[i]; }
+            BQ_UNROLL for (int i = 0; i < N; i++) { glag[i] = -glag[i]; wa[N + i] = xalt[i]; }
             csave = S.cauchy;
         }
     }
     if (csave > S.cauchy) {
-        BQ_NOUNROLL for (int i = 0; i < N; i++) xalt[i] = wa[N + i];
+        BQ_UNROLL for (int i = 0; i < N; i++) xalt[i] = wa[N + i];
         S.cauchy = csave;
     }
 }
@@ -345,20 +351,20 @@ BQ_HDN void altmov(State& S) {
 BQ_HD void hess_mul(const State& S, const double* s, double* hs) {
     BQ_ASSUME_SHARED(S);
     int ih = 0;
-    BQ_NOUNROLL for (int j = 0; j < N; j++) {
+    BQ_UNROLL for (int j = 0; j < N; j++) {
         hs[j] = 0.0;
-        BQ_NOUNROLL for (int i = 0; i <= j; i++) {
+        BQ_UNROLL for (int i = 0; i <= j; i++) {
             if (i < j) hs[j] += S.hq[ih] * s[i];
             hs[i] += S.hq[ih] * s[j];
             ih++;
         }
     }
-    BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
+    BQ_UNROLL for (int k = 0; k < NPT; k++) {
         if (S.pq[k] != 0.0) {
             double temp = 0.0;
-            BQ_NOUNROLL for (int j = 0; j < N; j++) temp += S.xpt[k][j] * s[j];
+            BQ_UNROLL for (int j = 0; j < N; j++) temp += S.xpt[k][j] * s[j];
             temp *= S.pq[k];
-            BQ_NOUNROLL for (int i = 0; i < N; i++) hs[i] += temp * S.xpt[k][i];
+            BQ_UNROLL for (int i = 0; i < N; i++) hs[i] += temp * S.xpt[k][i];
         }
     }
 }
@@ -483,7 +489,7 @@ BQ_HDN void trsbox(State& S, unsigned wmask) {
             }
             itcsav = iterc;
             hess_mul(S, s, hs);
-            BQ_NOUNROLL for (int i = 0; i < N; i++) hred[i] = hs[i];
+            BQ_UNROLL for (int i = 0; i < N; i++) hred[i] = hs[i];
             lbl = T_ALT_DIR;
             break;
         }
@@ -614,11 +620,11 @@ BQ_HDN void rescue_setup(State& S) {
     double sumpq = 0.0, winc = 0.0;
     BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
         double distsq = 0.0;
-        BQ_NOUNROLL for (int j = 0; j < N; j++) { xpt[k][j] -= xopt[j]; distsq += xpt[k][j] * xpt[k][j]; }
+        BQ_UNROLL for (int j = 0; j < N; j++) { xpt[k][j] -= xopt[j]; distsq += xpt[k][j] * xpt[k][j]; }
         sumpq += pq[k];
         wr[NDIM + k] = distsq;
         winc = dmax(winc, distsq);
-        BQ_NOUNROLL for (int j = 0; j < NPTM; j++) zmat[k][j] = 0.0;
+        BQ_UNROLL for (int j = 0; j < NPTM; j++) zmat[k][j] = 0.0;
     }
     {
         int ih = 0;
@@ -661,8 +667,8 @@ BQ_HDN void rescue_setup(State& S) {
     bool swap_phase = true;
     for (;;) {
         if (swap_phase) {
-            BQ_NOUNROLL for (int j = 0; j < N; j++) { const double t = bmat[kold][j]; bmat[kold][j] = bmat[knew][j]; bmat[knew][j] = t; }
-            BQ_NOUNROLL for (int j = 0; j < NPTM; j++) { const double t = zmat[kold][j]; zmat[kold][j] = zmat[knew][j]; zmat[knew][j] = t; }
+            BQ_UNROLL for (int j = 0; j < N; j++) { const double t = bmat[kold][j]; bmat[kold][j] = bmat[knew][j]; bmat[knew][j] = t; }
+            BQ_UNROLL for (int j = 0; j < NPTM; j++) { const double t = zmat[kold][j]; zmat[kold][j] = zmat[knew][j]; zmat[knew][j] = t; }
             ptsid[kold] = ptsid[knew];
             ptsid[knew] = 0.0;
             wr[NDIM + knew] = 0.0;
@@ -682,12 +688,12 @@ BQ_HDN void rescue_setup(State& S) {
             }
         }
         if (dsqmin == 0.0) break;
-        BQ_NOUNROLL for (int j = 0; j < N; j++) wr[NPT + j] = xpt[knew][j];
+        BQ_UNROLL for (int j = 0; j < N; j++) wr[NPT + j] = xpt[knew][j];
         BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
             double sum = 0.0;
             if (k == S.kopt) {
             } else if (ptsid[k] == 0.0) {
-                BQ_NOUNROLL for (int j = 0; j < N; j++) sum += wr[NPT + j] * xpt[k][j];
+                BQ_UNROLL for (int j = 0; j < N; j++) sum += wr[NPT + j] * xpt[k][j];
             } else {
                 const int ip = (int)ptsid[k];
                 if (ip > 0) sum = wr[NPT + ip - 1] * ptsaux[2 * (ip - 1)];
@@ -702,7 +708,7 @@ BQ_HDN void rescue_setup(State& S) {
         }
         BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
             double sum = 0.0;
-            BQ_NOUNROLL for (int j = 0; j < N; j++) sum += bmat[k][j] * wr[NPT + j];
+            BQ_UNROLL for (int j = 0; j < N; j++) sum += bmat[k][j] * wr[NPT + j];
             vlag[k] = sum;
         }
         beta = 0.0;
@@ -730,7 +736,7 @@ BQ_HDN void rescue_setup(State& S) {
         BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
             if (ptsid[k] != 0.0) {
                 double hdiag = 0.0;
-                BQ_NOUNROLL for (int j = 0; j < NPTM; j++) hdiag += zmat[k][j] * zmat[k][j];
+                BQ_UNROLL for (int j = 0; j < NPTM; j++) hdiag += zmat[k][j] * zmat[k][j];
                 const double den = beta * hdiag + vlag[k] * vlag[k];
                 if (den > denom) { kold = k; denom = den; }
             }
@@ -802,10 +808,10 @@ BQ_HDN void rescue_absorb(State& S, int kpt, double f) {
     double* hq = S.hq; double* pq = S.pq; double* gopt = S.gopt;
     double* ptsaux = S.w; double* ptsid = S.w + 6;
     const double diff = f - S.vquad_r;
-    BQ_NOUNROLL for (int i = 0; i < N; i++) gopt[i] += diff * bmat[kpt][i];
+    BQ_UNROLL for (int i = 0; i < N; i++) gopt[i] += diff * bmat[kpt][i];
     BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
         double sum = 0.0;
-        BQ_NOUNROLL for (int j = 0; j < NPTM; j++) sum += zmat[k][j] * zmat[kpt][j];
+        BQ_UNROLL for (int j = 0; j < NPTM; j++) sum += zmat[k][j] * zmat[kpt][j];
         const double temp = diff * sum;
         if (ptsid[k] == 0.0) pq[k] += temp;
         else {
@@ -851,9 +857,9 @@ BQ_HDN int start(State& S, const double* x0, const double* lb, const double* ub,
         if (lb[i] > ub[i] || x0[i] < lb[i] || x0[i] > ub[i]) { S.rc = R_INVALID_ARGS; S.pc = PC_FINISHED; return DONE; }
     }
     double dx[N];
-    BQ_NOUNROLL for (int i = 0; i < N; i++) dx[i] = default_step(lb[i], ub[i], x0[i]);
+    BQ_UNROLL for (int i = 0; i < N; i++) dx[i] = default_step(lb[i], ub[i], x0[i]);
     // rescale so that all initial steps equal dx[0]  (util/rescale.c:29-44)
-    BQ_NOUNROLL for (int i = 0; i < N; i++) S.scl[i] = 1.0;
+    BQ_UNROLL for (int i = 0; i < N; i++) S.scl[i] = 1.0;
     {
         int i = 1;
         BQ_NOUNROLL for (; i < N && dx[i] == dx[i - 1]; ++i) ;
@@ -890,20 +896,20 @@ BQ_HDN int start(State& S, const double* x0, const double* lb, const double* ub,
     BQ_NOUNROLL for (int ih = 0; ih < NH; ih++) S.hq[ih] = 0.0;
     BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
         S.pq[k] = 0.0;
-        BQ_NOUNROLL for (int j = 0; j < NPTM; j++) S.zmat[k][j] = 0.0;
+        BQ_UNROLL for (int j = 0; j < NPTM; j++) S.zmat[k][j] = 0.0;
     }
     S.nf = 0;
     S.pc = PC_PRELIM_EVAL;
     // emit the first point (the base point itself)
     S.nf = 1;
     point_from(S, S.xpt[0]);
-    BQ_NOUNROLL for (int i = 0; i < N; i++) xs_out[i] = S.x[i] * S.scl[i];
+    BQ_UNROLL for (int i = 0; i < N; i++) xs_out[i] = S.x[i] * S.scl[i];
     return ASK;
 }
 
 // final point in the caller's space (bobyqb exit block + unscale)
 BQ_HD void result_x(const State& S, double* xs_out) {
-    BQ_NOUNROLL for (int i = 0; i < N; i++) xs_out[i] = S.x[i] * S.scl[i];
+    BQ_UNROLL for (int i = 0; i < N; i++) xs_out[i] = S.x[i] * S.scl[i];
 }
 
 BQ_HDN int advance(State& S, double f_in, double* xs_out) {
@@ -976,12 +982,12 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
             }
             S.nf = nf2;
             point_from(S, xpt[nf2 - 1]);
-            BQ_NOUNROLL for (int i = 0; i < N; i++) xs_out[i] = S.x[i] * S.scl[i];
+            BQ_UNROLL for (int i = 0; i < N; i++) xs_out[i] = S.x[i] * S.scl[i];
             result = ASK; done = true;
         } else {
         // prelim finished (or ran out of evaluations): bobyqb start-up
         S.xoptsq = 0.0;
-        BQ_NOUNROLL for (int i = 0; i < N; i++) { xopt[i] = xpt[S.kopt][i]; S.xoptsq += xopt[i] * xopt[i]; }
+        BQ_UNROLL for (int i = 0; i < N; i++) { xopt[i] = xpt[S.kopt][i]; S.xoptsq += xopt[i] * xopt[i]; }
         S.fsave = fval[0];
         if (stop_evals) { S.rc = R_MAXEVAL_REACHED; lbl = L_EXIT; }
         else {
@@ -1025,6 +1031,10 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
 #else
         const unsigned sel = 0xffffffffu;
 #endif
+#if defined(__CUDA_ARCH__) && defined(HP_PROFILE)
+        const long long prof_t0 = clock64();
+        const int prof_lbl = lbl;
+#endif
         switch (lbl) {
         // -------------------------------------------------------------- gopt correction when kopt moved
         case L_GOPT_FIX: {
@@ -1039,9 +1049,9 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
                 if (S.nevals > NPT) {
                     BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
                         double temp = 0.0;
-                        BQ_NOUNROLL for (int j = 0; j < N; j++) temp += xpt[k][j] * xopt[j];
+                        BQ_UNROLL for (int j = 0; j < N; j++) temp += xpt[k][j] * xopt[j];
                         temp = pq[k] * temp;
-                        BQ_NOUNROLL for (int i = 0; i < N; i++) gopt[i] += temp * xpt[k][i];
+                        BQ_UNROLL for (int i = 0; i < N; i++) gopt[i] += temp * xpt[k][i];
                     }
                 }
             }
@@ -1089,7 +1099,7 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
                 BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
                     sumpq += pq[k];
                     double sum = -0.5 * xoptsq;
-                    BQ_NOUNROLL for (int i = 0; i < N; i++) sum += xpt[k][i] * xopt[i];
+                    BQ_UNROLL for (int i = 0; i < N; i++) sum += xpt[k][i] * xopt[i];
                     w[NPT + k] = sum;
                     const double temp = fracsq - 0.5 * sum;
                     BQ_NOUNROLL for (int i = 0; i < N; i++) {
@@ -1160,14 +1170,14 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
             S.kpt = kpt;
             rescue_place(S, kpt);
             S.pc = PC_RESCUE_EVAL;
-            BQ_NOUNROLL for (int i = 0; i < N; i++) xs_out[i] = S.x[i] * S.scl[i];
+            BQ_UNROLL for (int i = 0; i < N; i++) xs_out[i] = S.x[i] * S.scl[i];
             result = ASK; done = true;
             break;
         }
         case L_RESCUE_DONE: {
             S.xoptsq = 0.0;
             if (S.kopt != S.kbase) {
-                BQ_NOUNROLL for (int i = 0; i < N; i++) { xopt[i] = xpt[S.kopt][i]; S.xoptsq += xopt[i] * xopt[i]; }
+                BQ_UNROLL for (int i = 0; i < N; i++) { xopt[i] = xpt[S.kopt][i]; S.xoptsq += xopt[i] * xopt[i]; }
             }
             if (S.rc != R_SUCCESS) { lbl = L_EXIT; break; }
             S.nresc = S.nevals;
@@ -1179,7 +1189,7 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
         // -------------------------------------------------------------- alternative (geometry) step
         case L_ALTMOV: {
             altmov(S);
-            BQ_NOUNROLL for (int i = 0; i < N; i++) d[i] = xnew[i] - xopt[i];
+            BQ_UNROLL for (int i = 0; i < N; i++) d[i] = xnew[i] - xopt[i];
             lbl = L_VLAG;
             break;
         }
@@ -1210,7 +1220,7 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
                 BQ_NOUNROLL for (int k = 0; k < NPT; k++) sum += w[k] * bmat[k][j];
                 bsum += sum * d[j];
                 const int jp = NPT + j;
-                BQ_NOUNROLL for (int i = 0; i < N; i++) sum += bmat[jp][i] * d[i];
+                BQ_UNROLL for (int i = 0; i < N; i++) sum += bmat[jp][i] * d[i];
                 vlag[jp] = sum;
                 bsum += sum * d[j];
                 dx += d[j] * xopt[j];
@@ -1223,7 +1233,7 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
                 const double vk = vlag[S.knew];
                 S.denom = vk * vk + S.alpha * beta;
                 if (S.denom < S.cauchy && S.cauchy > 0.0) {
-                    BQ_NOUNROLL for (int i = 0; i < N; i++) { xnew[i] = xalt[i]; d[i] = xnew[i] - xopt[i]; }
+                    BQ_UNROLL for (int i = 0; i < N; i++) { xnew[i] = xalt[i]; d[i] = xnew[i] - xopt[i]; }
                     S.cauchy = 0.0;
                     lbl = L_VLAG;
                     break;
@@ -1241,10 +1251,10 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
                 BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
                     if (k == S.kopt) continue;
                     double hdiag = 0.0;
-                    BQ_NOUNROLL for (int jj = 0; jj < NPTM; jj++) hdiag += zmat[k][jj] * zmat[k][jj];
+                    BQ_UNROLL for (int jj = 0; jj < NPTM; jj++) hdiag += zmat[k][jj] * zmat[k][jj];
                     const double den = beta * hdiag + vlag[k] * vlag[k];
                     double distsq = 0.0;
-                    BQ_NOUNROLL for (int j = 0; j < N; j++) { const double t = xpt[k][j] - xopt[j]; distsq += t * t; }
+                    BQ_UNROLL for (int j = 0; j < N; j++) { const double t = xpt[k][j] - xopt[j]; distsq += t * t; }
                     const double r = distsq / delsq;
                     const double temp = dmax(1.0, r * r);
                     if (temp * den > scaden) { scaden = temp * den; S.knew = k; S.denom = den; }
@@ -1265,7 +1275,7 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
             point_from(S, xnew);
             if (S.maxeval > 0 && S.nevals >= S.maxeval) { S.rc = R_MAXEVAL_REACHED; lbl = L_EXIT; break; }
             S.pc = PC_MAIN_EVAL;
-            BQ_NOUNROLL for (int i = 0; i < N; i++) xs_out[i] = S.x[i] * S.scl[i];
+            BQ_UNROLL for (int i = 0; i < N; i++) xs_out[i] = S.x[i] * S.scl[i];
             result = ASK; done = true;
             break;
         }
@@ -1313,10 +1323,10 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
                     S.knew = -1;
                     BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
                         double hdiag = 0.0;
-                        BQ_NOUNROLL for (int jj = 0; jj < NPTM; jj++) hdiag += zmat[k][jj] * zmat[k][jj];
+                        BQ_UNROLL for (int jj = 0; jj < NPTM; jj++) hdiag += zmat[k][jj] * zmat[k][jj];
                         const double den = S.beta * hdiag + vlag[k] * vlag[k];
                         double distsq = 0.0;
-                        BQ_NOUNROLL for (int j = 0; j < N; j++) { const double t = xpt[k][j] - xnew[j]; distsq += t * t; }
+                        BQ_UNROLL for (int j = 0; j < N; j++) { const double t = xpt[k][j] - xnew[j]; distsq += t * t; }
                         const double r = distsq / delsq;
                         const double temp = dmax(1.0, r * r);
                         if (temp * den > scaden) { scaden = temp * den; S.knew = k; S.denom = den; }
@@ -1341,19 +1351,19 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
                 BQ_NOUNROLL for (int k = 0; k < NPT; k++) pq[k] += temp * zmat[k][jj];
             }
             fval[knew] = f;
-            BQ_NOUNROLL for (int i = 0; i < N; i++) { xpt[knew][i] = xnew[i]; w[i] = bmat[knew][i]; }
+            BQ_UNROLL for (int i = 0; i < N; i++) { xpt[knew][i] = xnew[i]; w[i] = bmat[knew][i]; }
             bool singular = false;
             BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
                 double suma = 0.0;
-                BQ_NOUNROLL for (int jj = 0; jj < NPTM; jj++) suma += zmat[knew][jj] * zmat[k][jj];
+                BQ_UNROLL for (int jj = 0; jj < NPTM; jj++) suma += zmat[knew][jj] * zmat[k][jj];
                 if (isinf(suma)) { singular = true; break; }
                 double sumb = 0.0;
-                BQ_NOUNROLL for (int j = 0; j < N; j++) sumb += xpt[k][j] * xopt[j];
+                BQ_UNROLL for (int j = 0; j < N; j++) sumb += xpt[k][j] * xopt[j];
                 const double temp = suma * sumb;
-                BQ_NOUNROLL for (int i = 0; i < N; i++) w[i] += temp * xpt[k][i];
+                BQ_UNROLL for (int i = 0; i < N; i++) w[i] += temp * xpt[k][i];
             }
             if (singular) { S.rc = R_ROUNDOFF_LIMITED; lbl = L_EXIT; break; }
-            BQ_NOUNROLL for (int i = 0; i < N; i++) gopt[i] += diff * w[i];
+            BQ_UNROLL for (int i = 0; i < N; i++) gopt[i] += diff * w[i];
             if (f < fopt) {
                 S.kopt = knew;
                 S.xoptsq = 0.0;
@@ -1369,9 +1379,9 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
                 }
                 BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
                     double temp = 0.0;
-                    BQ_NOUNROLL for (int j = 0; j < N; j++) temp += xpt[k][j] * d[j];
+                    BQ_UNROLL for (int j = 0; j < N; j++) temp += xpt[k][j] * d[j];
                     temp = pq[k] * temp;
-                    BQ_NOUNROLL for (int i = 0; i < N; i++) gopt[i] += temp * xpt[k][i];
+                    BQ_UNROLL for (int i = 0; i < N; i++) gopt[i] += temp * xpt[k][i];
                 }
                 // nlopt_stop_ftol never fires here: ftol_rel = ftol_abs = 0 on this path (util/stop.c:28-34)
             }
@@ -1385,7 +1395,7 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
                 }
                 BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
                     double sum = 0.0;
-                    BQ_NOUNROLL for (int j = 0; j < N; j++) sum += xpt[k][j] * xopt[j];
+                    BQ_UNROLL for (int j = 0; j < N; j++) sum += xpt[k][j] * xopt[j];
                     w[k + NPT] = w[k];
                     w[k] = sum * w[k];
                 }
@@ -1408,7 +1418,7 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
                 ++S.itest;
                 if (gqsq < 10.0 * gisq) S.itest = 0;
                 if (S.itest >= 3) {
-                    BQ_NOUNROLL for (int i = 0; i < N; i++) gopt[i] = vlag[NPT + i];
+                    BQ_UNROLL for (int i = 0; i < N; i++) gopt[i] = vlag[NPT + i];
                     BQ_NOUNROLL for (int k = 0; k < NPT; k++) pq[k] = w[NPT + k];
                     BQ_NOUNROLL for (int ih = 0; ih < NH; ih++) hq[ih] = 0.0;
                     S.itest = 0;
@@ -1428,7 +1438,7 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
             S.knew = -1;
             BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
                 double sum = 0.0;
-                BQ_NOUNROLL for (int j = 0; j < N; j++) { const double t = xpt[k][j] - xopt[j]; sum += t * t; }
+                BQ_UNROLL for (int j = 0; j < N; j++) { const double t = xpt[k][j] - xopt[j]; sum += t * t; }
                 if (sum > S.distsq) { S.knew = k; S.distsq = sum; }
             }
             if (S.knew >= 0) {
@@ -1479,6 +1489,17 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
             result = DONE; done = true;
             break;
         }
+#if defined(__CUDA_ARCH__) && defined(HP_PROFILE)
+        {
+            const unsigned now = __activemask();
+            unsigned lane_id; asm("mov.u32 %0, %%laneid;" : "=r"(lane_id));
+            if (lane_id == (unsigned)(__ffs(now) - 1)) {
+                atomicAdd(&g_prof_cycles[prof_lbl], (unsigned long long)(clock64() - prof_t0));
+                atomicAdd(&g_prof_trips[prof_lbl], 1ull);
+                atomicAdd(&g_prof_lanes[prof_lbl], (unsigned long long)__popc(now));
+            }
+        }
+#endif
     }
     return result;
 }
