@@ -325,6 +325,13 @@ def main():
         else:
             peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
         achieved = alg_bytes / mean_launch_s / 1e9
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+            if tj:
+                traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"])
+        except Exception:
+            traffic = None
         # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
         cpu = None
         if world == 1:
@@ -348,7 +355,7 @@ def main():
                         "ms_per_step": 1e3 * t_e2e_max / args.steps},
                 "gpu_launches": launches_timed,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "kernel": "hp::optimize_kernel",
+                             "traffic": traffic, "peak_source": peak_src, "kernel": "hp::optimize_kernel",
                              "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": 1e3 * mean_launch_s,
                              "note": "algorithmic gather bytes (588 B/texture, no reuse credit); the footprint is L1-resident so DRAM traffic is far lower - kernel is issue/latency bound, see DESIGN.md"},
                 "cpu_baseline": cpu}

@@ -458,6 +458,9 @@ int hpmvs_engine_counters(hpmvs_engine_t* e, hpmvs_counters_t* out, int reset) {
         unsigned long long pc[16], pt[16], pl[16];
         cudaMemcpyFromSymbol(pc, bq3::g_prof_cycles, sizeof(pc)); cudaMemcpyFromSymbol(pt, bq3::g_prof_trips, sizeof(pt));
         cudaMemcpyFromSymbol(pl, bq3::g_prof_lanes, sizeof(pl));
+        unsigned long long ev[8];
+        cudaMemcpyFromSymbol(ev, hp::g_eval_prof, sizeof(ev));
+        fprintf(stderr, "[hpmvs profile] eval Gcyc: setup %.2f sample %.2f stats %.2f normref %.2f dots %.2f\n", ev[0] / 1e9, ev[1] / 1e9, ev[2] / 1e9, ev[3] / 1e9, ev[4] / 1e9);
         const char* names[13] = {"AFTER_EVAL", "RESCUE_LOOP", "RESCUE_DONE", "GOPT_FIX", "FARPOINT", "REDUCE_RHO", "TRUST", "SHIFT", "RESCUE", "ALTMOV", "VLAG", "EVAL", "EXIT"};
         for (int i = 0; i < 13; i++)
             if (pt[i]) fprintf(stderr, "[hpmvs profile]   %-12s trips %10llu  cycles/trip %8.0f  lanes/trip %5.1f  total Gcyc %7.2f\n", names[i], pt[i], (double)pc[i] / pt[i], (double)pl[i] / pt[i], pc[i] / 1e9);

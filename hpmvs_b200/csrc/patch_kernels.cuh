@@ -36,6 +36,13 @@ constexpr int QS = 52;
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr unsigned FULL = 0xffffffffu;
 
+#ifdef HP_PROFILE
+__device__ unsigned long long g_eval_prof[8];
+#define HP_EVT(i, t0) do { if (lane == 0) atomicAdd(&g_eval_prof[i], (unsigned long long)(clock64() - (t0))); } while (0)
+#else
+#define HP_EVT(i, t0) do { } while (0)
+#endif
+
 // -DHP_PROFILE adds HP_CLOCK() accounting of optimizer / sampler time to counters[4..10] (see engine.cu)
 #ifdef HP_PROFILE
 #define HP_CLOCK() clock64()
@@ -82,12 +89,13 @@ struct ViewSetup {
 
 // per-warp scratch for one photometric evaluation
 struct __align__(16) Scratch {
-    float tex[VC][TEXS];
-    float q[VC][QS];
+    union {
+        float tex[VC][TEXS];            // raw -> normalised -> product textures of the views being evaluated
+        float rays[MAXV][4];            // view rays of the view-list stages (never live at the same time as tex)
+    };
     float mean[VC][4];
     float sigma[VC];
     int slot_view[VC];
-    float rays[MAXV][4];
     ViewSetup vs[MAXV];
     float dots[MAXV];
     float incc[MAXV];
@@ -102,6 +110,7 @@ struct __align__(16) LaneCtx {
     float center[4], normal[4];          // pCenter_, pNormal_
     float refCenter[4], refRay[4];       // refCenter_, refRay_
     float X0[4], Y0[4], Z0[4];           // imgX_[0], imgY_[0], imgZ_[0]
+    float xa[4], ya[4], za[4];           // pXaxis_, pYaxis_, pZaxis_ for the current centre / normal (objective only)
     double score;
     float scale;                         // pScale_
     int nimg;                            // pImages_.size()
@@ -232,29 +241,34 @@ __device__ __forceinline__ bool view_setup(const KParams& K, const DevCamera& ca
     return true;
 }
 
-// sampleTexture part 2 (:509-525): 49 samples, lane = sample (two passes); raw RGB goes to tex[slot]
-__device__ __forceinline__ void sample_view(Scratch& W, int slot, int k, int lane) {
-    const ViewSetup v = W.vs[k];
-    float* t = W.tex[slot];
+// sampleTexture part 2 (:509-525) for `ns` textures at once: the (slot, sample) pairs are flattened over the lanes,
+// two independent samples per lane and trip so that their loads and conversions overlap.  Raw RGB -> tex[slot].
+__device__ __forceinline__ void sample_one(Scratch& W, int idx) {
+    const int slot = idx / 49, s = idx - 49 * slot;
+    const ViewSetup& v = W.vs[W.slot_view[slot]];
+    const int yy = s / 7, xx = s - 7 * yy;
+    const float dyx = v.dyx, dyy = v.dyy, dxx = v.dxx, dxy = v.dxy;
+    float px = v.tlx, py = v.tly;
+    // the reference walks the grid with repeated f32 additions (l += dy; c += dx)
 #pragma unroll
-    for (int pass = 0; pass < 2; pass++) {
-        const int s = lane + 32 * pass;
-        if (s < 49) {
-            const int yy = s / 7, xx = s - 7 * yy;
-            float px = v.tlx, py = v.tly;
-            // the reference walks the grid with repeated f32 additions (l += dy; c += dx)
+    for (int i = 0; i < 6; i++) if (i < yy) { px += dyx; py += dyy; }
 #pragma unroll
-            for (int i = 0; i < 6; i++) if (i < yy) { px += v.dyx; py += v.dyy; }
-#pragma unroll
-            for (int i = 0; i < 6; i++) if (i < xx) { px += v.dxx; py += v.dxy; }
-            const f3 col = get_color(v.img, v.pitch, px, py);
-            t[3 * s] = col.x; t[3 * s + 1] = col.y; t[3 * s + 2] = col.z;
-        }
+    for (int i = 0; i < 6; i++) if (i < xx) { px += dxx; py += dxy; }
+    const f3 col = get_color(v.img, v.pitch, px, py);
+    float* t = W.tex[slot] + 3 * s;
+    t[0] = col.x; t[1] = col.y; t[2] = col.z;
+}
+__device__ __forceinline__ void sample_slots(Scratch& W, int first, int ns, int lane) {
+    const int beg = first * 49, end = (first + ns) * 49;
+    for (int base = beg + lane; base < end; base += 64) {
+        sample_one(W, base);
+        if (base + 32 < end) sample_one(W, base + 32);
     }
 }
 
-// PatchTex::normalize (Patch2d.hpp:46-84) for slots [first, first+ns): sequential chains, lane = (slot,channel)
-__device__ __forceinline__ void normalize_slots(Scratch& W, int first, int ns, int lane) {
+// PatchTex::normalize statistics (Patch2d.hpp:46-71) for slots [first, first+ns): per-channel means and the joint
+// standard deviation, each as the reference's SEQUENTIAL f32 chain (lane = one chain).
+__device__ __forceinline__ void stats_slots(Scratch& W, int first, int ns, int lane) {
     __syncwarp();
     if (lane < 3 * ns) {
         const int slot = first + lane / 3, ch = lane % 3;
@@ -265,40 +279,51 @@ __device__ __forceinline__ void normalize_slots(Scratch& W, int first, int ns, i
         W.mean[slot][ch] = a / 49.0f;
     }
     __syncwarp();
-    for (int idx = lane; idx < ns * 49; idx += 32) {
-        const int so = idx / 49, s = idx - 49 * so, slot = first + so;
-        const float* t = W.tex[slot] + 3 * s;
-        const float f0 = W.mean[slot][0] - t[0], f1 = W.mean[slot][1] - t[1], f2 = W.mean[slot][2] - t[2];
-        W.q[slot][s] = f0 * f0 + f1 * f1 + f2 * f2;
-    }
-    __syncwarp();
     if (lane < ns) {
         const int slot = first + lane;
-        const float* q = W.q[slot];
+        const float* t = W.tex[slot];
+        const float m0 = W.mean[slot][0], m1 = W.mean[slot][1], m2 = W.mean[slot][2];
         float a = 0.0f;
 #pragma unroll 7
-        for (int i = 0; i < 49; i++) a += q[i];
+        for (int i = 0; i < 49; i++) {
+            const float f0 = m0 - t[3 * i], f1 = m1 - t[3 * i + 1], f2 = m2 - t[3 * i + 2];
+            a += f0 * f0 + f1 * f1 + f2 * f2;
+        }
         float sg = sqrtf(a / 147.0f);
         if (sg == 0.0f) sg = 1.0f;
         W.sigma[slot] = sg;
     }
     __syncwarp();
-    for (int idx = lane; idx < ns * TEXN; idx += 32) {
-        const int so = idx / TEXN, i = idx - TEXN * so, slot = first + so;
-        const int ch = i % 3;
-        float v = W.tex[slot][i];
-        v -= W.mean[slot][ch];
-        v /= W.sigma[slot];
-        W.tex[slot][i] = v;
+}
+
+// normalise the reference texture in place (Patch2d.hpp:73-83)
+__device__ __forceinline__ void normalize_ref(Scratch& W, int lane) {
+    const float sg = W.sigma[0];
+    const float m[3] = {W.mean[0][0], W.mean[0][1], W.mean[0][2]};
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const int i = lane + 32 * k;
+        if (i < TEXN) {
+            float v = W.tex[0][i];
+            v -= m[i % 3];
+            v /= sg;
+            W.tex[0][i] = v;
+        }
     }
     __syncwarp();
 }
 
-// PatchTex::dot (Patch2d.hpp:37-44) of slot 0 with slots [1, 1+no): lane = slot for the 147-term chain
+// normalise slots [1, 1+no) and multiply with the normalised reference in one pass, then PatchTex::dot's
+// 147-term sequential chain (Patch2d.hpp:37-44), lane = slot
 __device__ __forceinline__ void dot_slots(Scratch& W, int no, int lane) {
-    for (int idx = lane; idx < no * TEXN; idx += 32) {
+    const int total = no * TEXN;
+#pragma unroll 4
+    for (int idx = lane; idx < total; idx += 32) {
         const int so = idx / TEXN, i = idx - TEXN * so, slot = 1 + so;
-        W.tex[slot][i] = W.tex[0][i] * W.tex[slot][i];
+        float v = W.tex[slot][i];
+        v -= W.mean[slot][i % 3];
+        v /= W.sigma[slot];
+        W.tex[slot][i] = W.tex[0][i] * v;
     }
     __syncwarp();
     if (lane < no) {
@@ -317,14 +342,19 @@ __device__ __forceinline__ void dot_slots(Scratch& W, int no, int lane) {
 // for patch context P (centre / normal / scale / view list) with view `refIdx` as reference, fill
 // W.vvalid[k] (sampleTexture succeeded) and W.dots[k] = refTex.dot(tex_k) for every valid k != refIdx.
 // If the reference view itself fails nothing else is sampled (both callers return early).
+// `axes_ready`: P.xa/ya/za already hold calculatePatchAxis for (P.images[0], P.normal) - the optimizer lane
+// computes them when it moves the patch, so the objective's critical path skips five normalisations.
 // ----------------------------------------------------------------------------------------------------------
-__device__ __noinline__ void eval_dots(Scratch& W, LaneCtx& P, const KParams& K, int lane, int refIdx, bool z_is_normal) {
+__device__ __noinline__ void eval_dots(Scratch& W, LaneCtx& P, const KParams& K, int lane, int refIdx, bool z_is_normal,
+                                       bool axes_ready) {
+    const long long t0 = HP_CLOCK();
     const int nimg = P.nimg;
     const f4 c = ld4(P.center);
     const f4 n = ld4(P.normal);
     const float scale = P.scale;
     f4 xa, ya, za;
-    patch_axes(K.cams[P.images[refIdx]], n, scale, xa, ya, za);
+    if (axes_ready) { xa = ld4(P.xa); ya = ld4(P.ya); za = ld4(P.za); }
+    else patch_axes(K.cams[P.images[refIdx]], n, scale, xa, ya, za);
     const f4 zgate = z_is_normal ? n : za;     // setINCCs passes pNormal_, objective_fn passes pZaxis_ (:456 vs :292)
     bool ok = false;
     if (lane < nimg) {
@@ -335,51 +365,69 @@ __device__ __noinline__ void eval_dots(Scratch& W, LaneCtx& P, const KParams& K,
     }
     const unsigned vmask = __ballot_sync(FULL, ok);
     __syncwarp();
+    HP_EVT(0, t0);
     if (!((vmask >> refIdx) & 1u)) return;
     // ordered list of valid non-reference views
     const unsigned omask = vmask & ~(1u << refIdx);
     if (ok && lane != refIdx) W.vlist[__popc(omask & ((1u << lane) - 1u))] = lane;
     const int nother = __popc(omask);
-    if (lane == 0) P.textures += 1 + nother;
+    if (lane == 0) { P.textures += 1 + nother; W.slot_view[0] = refIdx; }
     __syncwarp();
     // reference texture -> slot 0, then the others in groups of VC-1
     int done = 0;
     bool first = true;
     do {
         const int no = min(VC - 1, nother - done);
-        if (first) { sample_view(W, 0, refIdx, lane); }
-        for (int j = 0; j < no; j++) {
-            const int k = W.vlist[done + j];
-            if (lane == 0) W.slot_view[1 + j] = k;
-            sample_view(W, 1 + j, k, lane);
+        if (lane < no) W.slot_view[1 + lane] = W.vlist[done + lane];
+        __syncwarp();
+        const long long t1 = HP_CLOCK();
+        if (first) {
+            sample_slots(W, 0, 1 + no, lane);
+            __syncwarp();
+            HP_EVT(1, t1);
+            const long long t2 = HP_CLOCK();
+            stats_slots(W, 0, 1 + no, lane);
+            HP_EVT(2, t2);
+            const long long t3 = HP_CLOCK();
+            normalize_ref(W, lane);
+            HP_EVT(3, t3);
+        } else {
+            sample_slots(W, 1, no, lane);
+            stats_slots(W, 1, no, lane);
         }
-        if (first) normalize_slots(W, 0, 1 + no, lane);
-        else normalize_slots(W, 1, no, lane);
+        const long long t4 = HP_CLOCK();
         if (no > 0) dot_slots(W, no, lane);
+        HP_EVT(4, t4);
         done += no;
         first = false;
     } while (done < nother);
 }
 
-// objective_fn's reduction (:294-310), evaluated identically by every lane from shared values
-__device__ __forceinline__ double objective_value(const Scratch& W, const LaneCtx& P, const KParams& K) {
+// objective_fn's reduction (:294-310): robust value per view with lane = view, then the reference's sequential
+// f64 sum over the views in list order
+__device__ __forceinline__ double objective_value(Scratch& W, const LaneCtx& P, const KParams& K, int lane) {
     if (!W.vvalid[0]) return 2.0;
+    const int nimg = P.nimg;
+    if (lane >= 1 && lane < nimg && W.vvalid[lane]) {
+        const float r = (float)(1.0 - (double)W.dots[lane]);
+        W.incc[lane] = r / (1.0f + 3.0f * r);
+    }
+    __syncwarp();
     double val = 0.0;
     int nImgs = 0;
-    const int nimg = P.nimg;
     for (int ii = 1; ii < nimg; ii++) {
         if (!W.vvalid[ii]) continue;
-        const float r = (float)(1.0 - (double)W.dots[ii]);
-        val += (double)(r / (1.0f + 3.0f * r));
+        val += (double)W.incc[ii];
         nImgs++;
     }
+    __syncwarp();
     if (nImgs < K.opt.min_images_per_patch - 1) return 2.0;
     return val / nImgs;
 }
 
 // setINCCs (:448-474): lane = view
 __device__ __forceinline__ void set_inccs(Scratch& W, LaneCtx& P, const KParams& K, int lane, int refIdx, int robust) {
-    eval_dots(W, P, K, lane, refIdx, true);
+    eval_dots(W, P, K, lane, refIdx, true, false);
     if (lane < P.nimg) {
         float v;
         if (!W.vvalid[refIdx]) v = 2.0f;
@@ -611,6 +659,12 @@ __device__ __forceinline__ void set_center_norm(LaneCtx& P, const KParams& K, co
     const float fz = (float)(-c1 * c2);
     for (int i = 0; i < 3; i++) P.normal[i] = (P.X0[i] * fx + P.Y0[i] * fy) + P.Z0[i] * fz;
     P.normal[3] = 0.0f;
+    // calculatePatchAxis for the objective (objective_fn :289), done here lane-parallel for all moving patches
+    f4 xa, ya, za;
+    patch_axes(K.cams[P.images[0]], ld4(P.normal), P.scale, xa, ya, za);
+    P.xa[0] = xa.x; P.xa[1] = xa.y; P.xa[2] = xa.z; P.xa[3] = 0.0f;
+    P.ya[0] = ya.x; P.ya[1] = ya.y; P.ya[2] = ya.z; P.ya[3] = 0.0f;
+    P.za[0] = za.x; P.za[1] = za.y; P.za[2] = za.z; P.za[3] = 0.0f;
 }
 
 // setOptimizationFields + parametersFromCenterNorm (:384-399, :416-446): owning lane only
@@ -945,8 +999,8 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
             if (kind == REQ_EXIT) break;
             LaneCtx& P = C.ctx[slot];
             if (kind == REQ_EVAL) {
-                eval_dots(W, P, K, lane, 0, false);
-                const double f = objective_value(W, P, K);
+                eval_dots(W, P, K, lane, 0, false, true);
+                const double f = objective_value(W, P, K, lane);
                 __syncwarp();
                 if (lane == 0) {
                     *reinterpret_cast<volatile double*>(&C.fval[slot]) = f;
