@@ -34,9 +34,11 @@
 // innermost 3-trip loops with one-statement bodies (and hess_mul) ARE unrolled: the per-label cycle profile
 // (profiles/) showed the rolled multiply-accumulate loops costing ~10 instructions per MAC.
 #define BQ_UNROLL _Pragma("unroll")
+#define BQ_UNROLL4 _Pragma("unroll 4")
 #else
 #define BQ_NOUNROLL
 #define BQ_UNROLL
+#define BQ_UNROLL4
 #endif
 
 // Warp-converged dispatch of the label state machines below (device only).  Lanes of one warp run different
@@ -73,6 +75,9 @@ namespace bq3 {
 __device__ unsigned long long g_prof_cycles[16];
 __device__ unsigned long long g_prof_trips[16];
 __device__ unsigned long long g_prof_lanes[16];
+__device__ unsigned long long g_tprof_cycles[8];
+__device__ unsigned long long g_tprof_trips[8];
+__device__ unsigned long long g_tprof_lanes[8];
 #endif
 
 enum : int { N = 3, NPT = 7, NDIM = 10, NPTM = 3, NP = 4, NH = 6 };
@@ -371,13 +376,14 @@ BQ_HD void hess_mul(const State& S, const double* s, double* hs) {
 
 BQ_HDN void trsbox(State& S, unsigned wmask) {
     BQ_ASSUME_SHARED(S);
-    double* xopt = S.xopt; double* gopt = S.gopt; double* sl = S.sl; double* su = S.su;
-    double* xnew = S.xnew; double* d = S.d;
-    double* gnew = S.w; double* xbdi = S.w + 3; double* s = S.w + 6; double* hs = S.w + 9; double* hred = S.w + 12;
+    // All N-vectors of this routine live in registers (every loop over N below is fully unrolled so that the
+    // indices are static); shared memory is only read (xpt, hq, pq) until the results are stored at T_FINISH.
+    double xopt[N], gopt[N], sl[N], su[N], xnew[N], d[N], gnew[N], xbdi[N], s[N], hs[N], hred[N];
+    BQ_UNROLL for (int i = 0; i < N; i++) { xopt[i] = S.xopt[i]; gopt[i] = S.gopt[i]; sl[i] = S.sl[i]; su[i] = S.su[i]; s[i] = 0.0; hs[i] = 0.0; hred[i] = 0.0; }
     const double delta = S.delta;
     int iterc = 0, nact = 0, itermax = 0, itcsav = 0, iact = 0;
     double gredsq = 0, ggsav = 0, dredsq = 0, dredg = 0, sredg = 0, angbd = 0, xsav = 0, beta = 0, stepsq = 0;
-    BQ_NOUNROLL for (int i = 0; i < N; i++) {
+    BQ_UNROLL for (int i = 0; i < N; i++) {
         xbdi[i] = 0.0;
         if (xopt[i] <= sl[i]) { if (gopt[i] >= 0.0) xbdi[i] = -1.0; }
         else if (xopt[i] >= su[i]) { if (gopt[i] <= 0.0) xbdi[i] = 1.0; }
@@ -395,6 +401,10 @@ BQ_HDN void trsbox(State& S, unsigned wmask) {
     bool fin = false;
     for (;;) {
         BQ_SCHED_BEGIN(wmask, fin, lbl)
+#if defined(__CUDA_ARCH__) && defined(HP_PROFILE)
+        const long long tp0 = clock64();
+        const int tp_lbl = lbl;
+#endif
         switch (lbl) {
         case T_RESTART:
             beta = 0.0;
@@ -402,7 +412,7 @@ BQ_HDN void trsbox(State& S, unsigned wmask) {
             break;
         case T_DIRECTION: {
             stepsq = 0.0;
-            BQ_NOUNROLL for (int i = 0; i < N; i++) {
+            BQ_UNROLL for (int i = 0; i < N; i++) {
                 if (xbdi[i] != 0.0) s[i] = 0.0;
                 else if (beta == 0.0) s[i] = -gnew[i];
                 else s[i] = beta * s[i] - gnew[i];
@@ -417,7 +427,7 @@ BQ_HDN void trsbox(State& S, unsigned wmask) {
         }
         case T_CGSTEP: {
             double resid = delsq, ds = 0.0, shs = 0.0;
-            BQ_NOUNROLL for (int i = 0; i < N; i++)
+            BQ_UNROLL for (int i = 0; i < N; i++)
                 if (xbdi[i] == 0.0) { resid -= d[i] * d[i]; ds += s[i] * d[i]; shs += s[i] * hs[i]; }
             if (resid <= 0.0) { lbl = T_BOUNDARY; break; }
             double temp = sqrt(stepsq * resid + ds * ds);
@@ -427,7 +437,7 @@ BQ_HDN void trsbox(State& S, unsigned wmask) {
             double stplen = blen;
             if (shs > 0.0) stplen = dmin(blen, gredsq / shs);
             iact = 0;
-            BQ_NOUNROLL for (int i = 0; i < N; i++) {
+            BQ_UNROLL for (int i = 0; i < N; i++) {
                 if (s[i] != 0.0) {
                     const double xsum = xopt[i] + d[i];
                     if (s[i] > 0.0) temp = (su[i] - xsum) / s[i];
@@ -445,7 +455,7 @@ BQ_HDN void trsbox(State& S, unsigned wmask) {
                 }
                 ggsav = gredsq;
                 gredsq = 0.0;
-                BQ_NOUNROLL for (int i = 0; i < N; i++) {
+                BQ_UNROLL for (int i = 0; i < N; i++) {
                     gnew[i] += stplen * hs[i];
                     if (xbdi[i] == 0.0) gredsq += gnew[i] * gnew[i];
                     d[i] += stplen * s[i];
@@ -455,9 +465,12 @@ BQ_HDN void trsbox(State& S, unsigned wmask) {
             }
             if (iact > 0) {
                 ++nact;
-                xbdi[iact - 1] = 1.0;
-                if (s[iact - 1] < 0.0) xbdi[iact - 1] = -1.0;
-                delsq -= d[iact - 1] * d[iact - 1];
+                BQ_UNROLL for (int i = 0; i < N; i++)
+                    if (i == iact - 1) {
+                        xbdi[i] = 1.0;
+                        if (s[i] < 0.0) xbdi[i] = -1.0;
+                        delsq -= d[i] * d[i];
+                    }
                 if (delsq <= 0.0) { lbl = T_BOUNDARY; break; }
                 lbl = T_RESTART;
                 break;
@@ -479,7 +492,7 @@ BQ_HDN void trsbox(State& S, unsigned wmask) {
         case T_ALT_PREP: {
             if (nact >= N - 1) { lbl = T_FINISH; break; }
             dredsq = 0.0; dredg = 0.0; gredsq = 0.0;
-            BQ_NOUNROLL for (int i = 0; i < N; i++) {
+            BQ_UNROLL for (int i = 0; i < N; i++) {
                 if (xbdi[i] == 0.0) {
                     dredsq += d[i] * d[i];
                     dredg += d[i] * gnew[i];
@@ -498,7 +511,7 @@ BQ_HDN void trsbox(State& S, unsigned wmask) {
             double temp = gredsq * dredsq - dredg * dredg;
             if (temp <= qred * 1e-4 * qred) { lbl = T_FINISH; break; }
             temp = sqrt(temp);
-            BQ_NOUNROLL for (int i = 0; i < N; i++) {
+            BQ_UNROLL for (int i = 0; i < N; i++) {
                 if (xbdi[i] == 0.0) s[i] = (dredg * d[i] - dredsq * gnew[i]) / temp;
                 else s[i] = 0.0;
             }
@@ -506,7 +519,7 @@ BQ_HDN void trsbox(State& S, unsigned wmask) {
             angbd = 1.0;
             iact = 0;
             bool refix = false;
-            BQ_NOUNROLL for (int i = 0; i < N; i++) {
+            BQ_UNROLL for (int i = 0; i < N; i++) {
                 if (xbdi[i] == 0.0) {
                     const double tempa = xopt[i] + d[i] - sl[i];
                     const double tempb = su[i] - xopt[i] - d[i];
@@ -534,7 +547,7 @@ BQ_HDN void trsbox(State& S, unsigned wmask) {
         }
         case T_ALT_SEARCH: {
             double shs = 0.0, dhs = 0.0, dhd = 0.0;
-            BQ_NOUNROLL for (int i = 0; i < N; i++)
+            BQ_UNROLL for (int i = 0; i < N; i++)
                 if (xbdi[i] == 0.0) { shs += s[i] * hs[i]; dhs += d[i] * hs[i]; dhd += d[i] * hred[i]; }
             double redmax = 0.0, redsav = 0.0, rdprev = 0.0, rdnext = 0.0;
             int isav = 0;
@@ -562,7 +575,7 @@ BQ_HDN void trsbox(State& S, unsigned wmask) {
             const double sdec = sth * (angt * dredg - sredg - 0.5 * sth * temp);
             if (sdec <= 0.0) { lbl = T_FINISH; break; }
             dredg = 0.0; gredsq = 0.0;
-            BQ_NOUNROLL for (int i = 0; i < N; i++) {
+            BQ_UNROLL for (int i = 0; i < N; i++) {
                 gnew[i] = gnew[i] + (cth - 1.0) * hred[i] + sth * hs[i];
                 if (xbdi[i] == 0.0) {
                     d[i] = cth * d[i] + sth * s[i];
@@ -572,14 +585,19 @@ BQ_HDN void trsbox(State& S, unsigned wmask) {
                 hred[i] = cth * hred[i] + sth * hs[i];
             }
             qred += sdec;
-            if (iact > 0 && isav == iu) { ++nact; xbdi[iact - 1] = xsav; lbl = T_ALT_PREP; break; }
+            if (iact > 0 && isav == iu) {
+                ++nact;
+                BQ_UNROLL for (int i = 0; i < N; i++) if (i == iact - 1) xbdi[i] = xsav;
+                lbl = T_ALT_PREP;
+                break;
+            }
             if (sdec > qred * 0.01) { lbl = T_ALT_DIR; break; }
             lbl = T_FINISH;
             break;
         }
         case T_FINISH: {
             double dsq = 0.0;
-            BQ_NOUNROLL for (int i = 0; i < N; i++) {
+            BQ_UNROLL for (int i = 0; i < N; i++) {
                 xnew[i] = dmax(dmin(xopt[i] + d[i], su[i]), sl[i]);
                 if (xbdi[i] == -1.0) xnew[i] = sl[i];
                 if (xbdi[i] == 1.0) xnew[i] = su[i];
@@ -588,10 +606,25 @@ BQ_HDN void trsbox(State& S, unsigned wmask) {
             }
             S.dsq = dsq;
             S.crvmin = crvmin;
+            BQ_UNROLL for (int i = 0; i < N; i++) {
+                S.xnew[i] = xnew[i]; S.d[i] = d[i];
+                S.w[i] = gnew[i]; S.w[3 + i] = xbdi[i]; S.w[6 + i] = s[i]; S.w[9 + i] = hs[i]; S.w[12 + i] = hred[i];
+            }
             fin = true;
             break;
         }
         }
+#if defined(__CUDA_ARCH__) && defined(HP_PROFILE)
+        {
+            const unsigned now = __activemask();
+            unsigned lane_id; asm("mov.u32 %0, %%laneid;" : "=r"(lane_id));
+            if (lane_id == (unsigned)(__ffs(now) - 1)) {
+                atomicAdd(&g_tprof_cycles[tp_lbl], (unsigned long long)(clock64() - tp0));
+                atomicAdd(&g_tprof_trips[tp_lbl], 1ull);
+                atomicAdd(&g_tprof_lanes[tp_lbl], (unsigned long long)__popc(now));
+            }
+        }
+#endif
     }
 }
 

@@ -90,7 +90,8 @@ struct KernelVariant {
 #define HP_VARIANT(OW, SW, LPW) {OW, SW, LPW, hp::optimize_kernel<OW, SW, LPW>, sizeof(hp::CtaSharedT<OW, SW, LPW>)}
 static const KernelVariant g_variants[] = {HP_VARIANT(2, 10, 32), HP_VARIANT(2, 8, 32), HP_VARIANT(2, 6, 32), HP_VARIANT(4, 8, 16),
                                            HP_VARIANT(4, 10, 16), HP_VARIANT(8, 8, 8), HP_VARIANT(8, 10, 8), HP_VARIANT(4, 12, 12),
-                                           HP_VARIANT(6, 10, 10), HP_VARIANT(1, 8, 32), HP_VARIANT(3, 10, 20)};
+                                           HP_VARIANT(6, 10, 10), HP_VARIANT(1, 8, 32), HP_VARIANT(3, 10, 20), HP_VARIANT(3, 10, 23), HP_VARIANT(3, 10, 24),
+                                           HP_VARIANT(3, 9, 24), HP_VARIANT(3, 12, 23), HP_VARIANT(2, 12, 32), HP_VARIANT(2, 14, 32)};
 static const int g_default_variant = 0;
 
 static int ensure_patch_capacity(hpmvs_engine* e, size_t n) {
@@ -461,6 +462,12 @@ int hpmvs_engine_counters(hpmvs_engine_t* e, hpmvs_counters_t* out, int reset) {
         unsigned long long ev[8];
         cudaMemcpyFromSymbol(ev, hp::g_eval_prof, sizeof(ev));
         fprintf(stderr, "[hpmvs profile] eval Gcyc: setup %.2f sample %.2f stats %.2f normref %.2f dots %.2f\n", ev[0] / 1e9, ev[1] / 1e9, ev[2] / 1e9, ev[3] / 1e9, ev[4] / 1e9);
+        {
+            unsigned long long tc[8], tt[8], tl[8];
+            cudaMemcpyFromSymbol(tc, bq3::g_tprof_cycles, sizeof(tc)); cudaMemcpyFromSymbol(tt, bq3::g_tprof_trips, sizeof(tt)); cudaMemcpyFromSymbol(tl, bq3::g_tprof_lanes, sizeof(tl));
+            const char* tn[8] = {"T_RESTART", "T_DIRECTION", "T_CGSTEP", "T_BOUNDARY", "T_ALT_PREP", "T_ALT_DIR", "T_ALT_SEARCH", "T_FINISH"};
+            for (int i = 0; i < 8; i++) if (tt[i]) fprintf(stderr, "[hpmvs profile]     trsbox %-12s trips %10llu cycles/trip %7.0f lanes/trip %5.1f total Gcyc %7.2f\n", tn[i], tt[i], (double)tc[i] / tt[i], (double)tl[i] / tt[i], tc[i] / 1e9);
+        }
         const char* names[13] = {"AFTER_EVAL", "RESCUE_LOOP", "RESCUE_DONE", "GOPT_FIX", "FARPOINT", "REDUCE_RHO", "TRUST", "SHIFT", "RESCUE", "ALTMOV", "VLAG", "EVAL", "EXIT"};
         for (int i = 0; i < 13; i++)
             if (pt[i]) fprintf(stderr, "[hpmvs profile]   %-12s trips %10llu  cycles/trip %8.0f  lanes/trip %5.1f  total Gcyc %7.2f\n", names[i], pt[i], (double)pc[i] / pt[i], (double)pl[i] / pt[i], pc[i] / 1e9);
