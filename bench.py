@@ -59,7 +59,12 @@ def workload_scene(name: str, rank: int = 0):
     if name == "tiny":
         return synth.plane_scene(n_views=8, width=640, height=480, focal=600.0, n_seeds=2000, seed=2, point_seed=2 + 1000 * rank,
                                  tex_size=512), "8-view 640x480 synthetic plane, 2k seed patches (smoke size)"
-    return synth.city_scene(n_views=100, width=1920, height=1080, n_seeds=100000, seed=4 + 1000 * rank), \
+    try:
+        import torch
+        synth.USE_GPU_RENDERER = torch.cuda.is_available()    # 100 x 1080p ray casts: seconds on the GPU, minutes in numpy
+    except ImportError:
+        pass
+    return synth.city_scene(n_views=100, width=1920, height=1080, n_seeds=100000, seed=4, name="city100v"), \
         "100-view 1080p synthetic city block, 100k seed patches (BASELINE.json configs[3] on 1 GPU)"
 
 

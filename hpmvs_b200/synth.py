@@ -121,8 +121,61 @@ def _bilinear(tex: np.ndarray, u: np.ndarray, v: np.ndarray) -> np.ndarray:
     return a * (1 - fy) + b * fy
 
 
+USE_GPU_RENDERER = False     # bench.py turns this on for the large scenes; tests / goldens always use numpy (bit-reproducible)
+
+
 def render(cam: NVMCamera, quads: List[Quad], background: int = 30, supersample: int = 1) -> np.ndarray:
-    """Exact inverse ray casting of textured quads; nearest hit wins. Returns u8 [H,W,3]."""
+    """Exact inverse ray casting of textured quads; nearest hit wins. Returns u8 [H,W,3].
+    Uses the GPU (torch, float64) when one is present - the 100-view scenes would take minutes in numpy."""
+    try:
+        import torch
+        if USE_GPU_RENDERER and torch.cuda.is_available() and supersample == 1:
+            return _render_torch(cam, quads, background)
+    except ImportError:
+        pass
+    return _render_numpy(cam, quads, background, supersample)
+
+
+def _render_torch(cam: NVMCamera, quads: List[Quad], background: int) -> np.ndarray:
+    import torch
+    dev = torch.device("cuda")
+    f64 = torch.float64
+    W, H = cam.width, cam.height
+    R = torch.tensor(cam.rotation(), dtype=f64, device=dev)
+    c = torch.tensor(cam.c, dtype=f64, device=dev)
+    us = torch.arange(W, dtype=f64, device=dev)
+    vs = torch.arange(H, dtype=f64, device=dev)
+    vv, uu = torch.meshgrid(vs, us, indexing="ij")
+    d_cam = torch.stack([(uu - W / 2.0) / cam.f, (vv - H / 2.0) / cam.f, torch.ones_like(uu)], -1)
+    d = d_cam @ R
+    out = torch.full((H, W, 3), float(background), dtype=f64, device=dev)
+    depth = torch.full((H, W), float("inf"), dtype=f64, device=dev)
+    for q in quads:
+        eu = torch.tensor(q.eu, dtype=f64, device=dev); ev = torch.tensor(q.ev, dtype=f64, device=dev)
+        o = torch.tensor(q.origin, dtype=f64, device=dev)
+        n = torch.linalg.cross(eu, ev)
+        denom = d @ n
+        t = ((o - c) @ n) / denom
+        X = c + t[..., None] * d
+        rel = X - o
+        lu = (rel @ eu) / (eu @ eu)
+        lv = (rel @ ev) / (ev @ ev)
+        hit = (t > 1e-6) & (lu >= 0) & (lu <= 1) & (lv >= 0) & (lv <= 1) & (t < depth) & torch.isfinite(t)
+        if not bool(hit.any()):
+            continue
+        tex = torch.from_numpy(q.tex).to(dev).to(f64)
+        T = tex.shape[0]
+        x = torch.clamp(lu[hit] * (T - 1), 0, T - 1 - 1e-9); y = torch.clamp(lv[hit] * (T - 1), 0, T - 1 - 1e-9)
+        x0 = x.long(); y0 = y.long()
+        fx = (x - x0)[..., None]; fy = (y - y0)[..., None]
+        a = tex[y0, x0] * (1 - fx) + tex[y0, x0 + 1] * fx
+        b = tex[y0 + 1, x0] * (1 - fx) + tex[y0 + 1, x0 + 1] * fx
+        out[hit] = a * (1 - fy) + b * fy
+        depth[hit] = t[hit]
+    return torch.clamp(torch.round(out), 0, 255).to(torch.uint8).cpu().numpy()
+
+
+def _render_numpy(cam: NVMCamera, quads: List[Quad], background: int = 30, supersample: int = 1) -> np.ndarray:
     W, H = cam.width, cam.height
     R = cam.rotation()
     ss = supersample
@@ -229,6 +282,72 @@ def _attach_measurements(name, cams, images, pts, quads, margin: float, max_meas
                       np.asarray(mc, np.int32), quads)
 
 
+def _measure_visibility(cams, quads, surf, nrm, pick):
+    """vis[i,c]: surface point i is inside view c, un-occluded (ray cast against every quad) and within 65 deg of
+    its face normal; cosang[i,c] = |cos| of that angle.  Vectorised over (points x quads); torch on the GPU if enabled."""
+    n_seeds, n_views = surf.shape[0], len(cams)
+    org = np.stack([q.origin for q in quads]); eus = np.stack([q.eu for q in quads]); evs = np.stack([q.ev for q in quads])
+    nq = np.cross(eus, evs)
+    use_torch = False
+    if USE_GPU_RENDERER:
+        try:
+            import torch
+            use_torch = torch.cuda.is_available()
+        except ImportError:
+            use_torch = False
+    vis = np.zeros((n_seeds, n_views), bool)
+    cosang = np.zeros((n_seeds, n_views))
+    cos_lim = math.cos(math.radians(65.0))
+    if use_torch:
+        import torch
+        dev, f64 = torch.device("cuda"), torch.float64
+        T = lambda a: torch.tensor(a, dtype=f64, device=dev)
+        surf_t, nrm_t, org_t, eu_t, ev_t, nq_t = T(surf), T(nrm), T(org), T(eus), T(evs), T(nq)
+        pick_t = torch.tensor(pick, device=dev)
+        qid = torch.arange(len(quads), device=dev)[None, :]
+        euu = (eu_t * eu_t).sum(1); evv = (ev_t * ev_t).sum(1)
+    for ci, cam in enumerate(cams):
+        inside = _visible(cam, surf, 60.0)
+        if use_torch:
+            c = T(cam.c)
+            ray = surf_t - c
+            dist = ray.norm(dim=1)
+            dirs = ray / dist[:, None]
+            cosv = (-(dirs * nrm_t).sum(1)).abs()
+            occ = torch.zeros(n_seeds, dtype=torch.bool, device=dev)
+            for a in range(0, n_seeds, 20000):
+                dd = dirs[a:a + 20000]
+                denom = dd @ nq_t.T
+                t = (((org_t - c) * nq_t).sum(1))[None, :] / denom
+                X = c + t[..., None] * dd[:, None, :]
+                rel = X - org_t[None]
+                lu = (rel * eu_t[None]).sum(-1) / euu[None]; lv = (rel * ev_t[None]).sum(-1) / evv[None]
+                hit = torch.isfinite(t) & (t > 1e-6) & (t < dist[a:a + 20000, None] - 1e-3) & (lu >= 0) & (lu <= 1) & (lv >= 0) & (lv <= 1) & \
+                    (pick_t[a:a + 20000, None] != qid)
+                occ[a:a + 20000] = hit.any(1)
+            occluded = occ.cpu().numpy(); cosv = cosv.cpu().numpy()
+        else:
+            ray = surf - cam.c
+            dist = np.linalg.norm(ray, axis=1)
+            dirs = ray / dist[:, None]
+            cosv = np.abs(np.einsum("ij,ij->i", -dirs, nrm))
+            occluded = np.zeros(n_seeds, bool)
+            for a in range(0, n_seeds, 20000):
+                dd = dirs[a:a + 20000]
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    denom = dd @ nq.T
+                    t = (((org - cam.c) * nq).sum(1))[None, :] / denom
+                    X = cam.c + t[..., None] * dd[:, None, :]
+                    rel = X - org[None]
+                    lu = (rel * eus[None]).sum(-1) / (eus * eus).sum(1)[None]; lv = (rel * evs[None]).sum(-1) / (evs * evs).sum(1)[None]
+                    hit = np.isfinite(t) & (t > 1e-6) & (t < dist[a:a + 20000, None] - 1e-3) & (lu >= 0) & (lu <= 1) & (lv >= 0) & (lv <= 1) & \
+                        (pick[a:a + 20000, None] != np.arange(len(quads))[None, :])
+                occluded[a:a + 20000] = hit.any(1)
+        vis[:, ci] = inside & ~occluded & (cosv > cos_lim)
+        cosang[:, ci] = cosv
+    return vis, cosang
+
+
 def box_quads(center, size, seed: int, tex_size: int = 512) -> List[Quad]:
     """5 visible faces (no bottom) of an axis-aligned box, each with its own texture."""
     cx, cy, cz = center
@@ -273,12 +392,25 @@ def city_scene(n_views: int = 100, width: int = 1920, height: int = 1080, focal:
     areas[0] *= 0.15
     pick = rng.choice(len(quads), n_seeds, p=areas / areas.sum())
     uv = rng.random((n_seeds, 2)) * 0.9 + 0.05
-    pts = np.stack([quads[k].origin + uv[i, 0] * quads[k].eu + uv[i, 1] * quads[k].ev for i, k in enumerate(pick)], 0)
-    nrm = np.stack([quads[k].normal for k in pick], 0)
+    org = np.stack([q.origin for q in quads]); eus = np.stack([q.eu for q in quads]); evs = np.stack([q.ev for q in quads])
+    surf = org[pick] + uv[:, :1] * eus[pick] + uv[:, 1:] * evs[pick]
+    nrm = np.stack([q.normal for q in quads])[pick]
     scale = 16.0 * loop_radius / focal
-    pts = pts + nrm * rng.normal(0, 0.3 * scale, n_seeds)[:, None]
-    return _attach_measurements(name or f"city{n_views}v", cams, images, pts, quads, margin=60.0,
-                                max_meas=max_meas, rng=rng)
+    pts = surf + nrm * rng.normal(0, 0.3 * scale, n_seeds)[:, None]
+    # measurements: un-occluded, front-facing views only (ray cast against every quad), most frontal first
+    vis, cosang = _measure_visibility(cams, quads, surf, nrm, pick)
+    offs = [0]
+    mc: List[int] = []
+    for i in range(n_seeds):
+        ids = np.nonzero(vis[i])[0]
+        if len(ids) > max_meas:
+            ids = ids[np.argsort(-cosang[i, ids], kind="stable")[:max_meas]]
+        else:
+            ids = ids[np.argsort(-cosang[i, ids], kind="stable")]
+        mc.extend(int(v) for v in ids)
+        offs.append(len(mc))
+    return SynthScene(name or f"city{n_views}v", cams, images, pts.astype(np.float64), np.asarray(offs, np.int32),
+                      np.asarray(mc, np.int32), quads)
 
 
 # --------------------------------------------------------------------------------------------
