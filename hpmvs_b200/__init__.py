@@ -4,8 +4,8 @@ Everything computational lives in libhpmvs_b200.so (hand-written sm_100a CUDA + 
 this package is the thin Python plumbing used by the tests and bench.py.
 """
 from .engine import (Camera, Counters, Engine, HpmvsError, Options, PATCH_DTYPE, STATUS_NAMES, MAX_VIEWS, LEVELS,
-                     camera_from_nvm, extract_covis, seed_patches)
+                     camera_from_nvm, expand_candidates, extract_covis, seed_patches)
 from . import synth  # noqa: F401
 
 __all__ = ["Camera", "Counters", "Engine", "HpmvsError", "Options", "PATCH_DTYPE", "STATUS_NAMES", "MAX_VIEWS", "LEVELS",
-           "camera_from_nvm", "extract_covis", "seed_patches", "synth"]
+           "camera_from_nvm", "expand_candidates", "extract_covis", "seed_patches", "synth"]

@@ -58,6 +58,9 @@ struct hpmvs_engine {
     int ncams = 0;
     std::vector<hp::DevCamera> h_cams;
     std::vector<std::vector<LevelImage>> images;   // [cam][level]
+    std::vector<std::vector<float*>> depths;        // [cam][level] Scene::m_depths
+    int* d_accept = nullptr;
+    size_t cap_accept = 0;
     hp::DevCamera* d_cams = nullptr;
     bool cams_dirty = true;
     int* d_covis_off = nullptr;
@@ -114,6 +117,9 @@ static int sync_cameras(hpmvs_engine* e) {
             const LevelImage& li = e->images[c][l];
             e->h_cams[c].img[l] = li.data;
             e->h_cams[c].pitch[l] = li.pitch;
+            e->h_cams[c].depth[l] = (c < (int)e->depths.size() && l < (int)e->depths[c].size()) ? e->depths[c][l] : nullptr;
+            e->h_cams[c].drows[l] = (int)(e->h_cams[c].h[l] / 2.0);     // Scene.cpp:76-77 (DEPTH_SUBSAMPLE is a double)
+            e->h_cams[c].dcols[l] = (int)(e->h_cams[c].w[l] / 2.0);
         }
     HP_CUDA(cudaMemcpyAsync(e->d_cams, e->h_cams.data(), sizeof(hp::DevCamera) * e->ncams, cudaMemcpyHostToDevice, e->stream));
     HP_CUDA(cudaStreamSynchronize(e->stream));
@@ -212,6 +218,10 @@ void hpmvs_engine_destroy(hpmvs_engine_t* e) {
     for (auto& cam : e->images)
         for (auto& li : cam)
             if (li.data) cudaFree(li.data);
+    for (auto& cam : e->depths)
+        for (auto* d : cam)
+            if (d) cudaFree(d);
+    cudaFree(e->d_accept);
     cudaFree(e->d_cams); cudaFree(e->d_covis_off); cudaFree(e->d_covis_ids);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_inccs); cudaFree(e->d_stage);
     cudaFree(e->d_work); cudaFree(e->d_counters);
@@ -443,6 +453,92 @@ int hpmvs_ncc_batch(hpmvs_engine_t* e, int n, const hpmvs_patch_t* in, int ref_i
     HP_CUDA(cudaGetLastError());
     HP_CUDA(cudaMemcpyAsync(inccs, e->d_inccs, ni * sizeof(float), cudaMemcpyDeviceToHost, s));
     HP_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// ---- "next" row f-2: depth maps + acceptance tests -----------------------------------------------------------
+int hpmvs_engine_depth_reset(hpmvs_engine_t* e) {
+    if (!e) return HPMVS_E_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    HP_CUDA(cudaSetDevice(e->device));
+    if (e->ncams <= 0) return HPMVS_E_STATE;
+    const int nl = e->opt.maxlevel + 1;
+    if ((int)e->depths.size() != e->ncams) {
+        for (auto& cam : e->depths) for (auto* d : cam) if (d) cudaFree(d);
+        e->depths.assign(e->ncams, std::vector<float*>(HPMVS_LEVELS, nullptr));
+        e->cams_dirty = true;
+    }
+    for (int c = 0; c < e->ncams; c++)
+        for (int l = 0; l < nl; l++) {
+            const size_t rows = (size_t)(int)(e->h_cams[c].h[l] / 2.0), cols = (size_t)(int)(e->h_cams[c].w[l] / 2.0);
+            const size_t cnt = rows * cols > 0 ? rows * cols : 1;
+            if (!e->depths[c][l]) { HP_CUDA(cudaMalloc(&e->depths[c][l], cnt * sizeof(float))); e->cams_dirty = true; }
+            hp::depth_fill_kernel<<<(unsigned)((cnt + 255) / 256 > 1024 ? 1024 : (cnt + 255) / 256), 256, 0, e->stream>>>(e->depths[c][l], cnt);
+            e->launches++;
+        }
+    HP_CUDA(cudaGetLastError());
+    HP_CUDA(cudaStreamSynchronize(e->stream));
+    return sync_cameras(e);
+}
+
+static int ensure_depths(hpmvs_engine* e) {
+    if ((int)e->depths.size() == e->ncams && e->ncams > 0 && e->depths[0][0]) return 0;
+    return HPMVS_E_STATE;
+}
+
+int hpmvs_depth_set_batch(hpmvs_engine_t* e, int n, const hpmvs_patch_t* patches, void* stream) {
+    if (!e || n < 0 || (n > 0 && !patches)) return HPMVS_E_ARG;
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(e->mu);
+    HP_CUDA(cudaSetDevice(e->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    int rc = ensure_depths(e); if (rc) return rc;
+    rc = sync_cameras(e); if (rc) return rc;
+    rc = ensure_patch_capacity(e, (size_t)n); if (rc) return rc;
+    HP_CUDA(cudaMemcpyAsync(e->d_in, patches, sizeof(hpmvs_patch_t) * n, cudaMemcpyHostToDevice, s));
+    const hp::KParams K = make_params(e, e->d_in, e->d_out, n);
+    const int total = n * HPMVS_MAX_VIEWS;
+    hp::depth_set_kernel<<<(total + 255) / 256, 256, 0, s>>>(K, e->d_in, n);
+    e->launches++;
+    HP_CUDA(cudaGetLastError());
+    HP_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int hpmvs_accept_batch(hpmvs_engine_t* e, int n, const hpmvs_patch_t* patches, float margin, int32_t* out, void* stream) {
+    if (!e || n < 0 || (n > 0 && (!patches || !out))) return HPMVS_E_ARG;
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(e->mu);
+    HP_CUDA(cudaSetDevice(e->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    int rc = ensure_depths(e); if (rc) return rc;
+    rc = sync_cameras(e); if (rc) return rc;
+    rc = ensure_patch_capacity(e, (size_t)n); if (rc) return rc;
+    if ((size_t)n * 3 > e->cap_accept) {
+        if (e->d_accept) cudaFree(e->d_accept);
+        e->d_accept = nullptr; e->cap_accept = 0;
+        HP_CUDA(cudaMalloc(&e->d_accept, sizeof(int) * 3 * ((size_t)n + 1024)));
+        e->cap_accept = 3 * ((size_t)n + 1024);
+    }
+    HP_CUDA(cudaMemcpyAsync(e->d_in, patches, sizeof(hpmvs_patch_t) * n, cudaMemcpyHostToDevice, s));
+    const hp::KParams K = make_params(e, e->d_in, e->d_out, n);
+    int grid = (n + 7) / 8;
+    if (grid > e->sm_count * 8) grid = e->sm_count * 8;
+    hp::accept_kernel<<<grid, 256, 0, s>>>(K, e->d_in, n, margin, e->d_accept);
+    e->launches++;
+    HP_CUDA(cudaGetLastError());
+    HP_CUDA(cudaMemcpyAsync(out, e->d_accept, sizeof(int) * 3 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    HP_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int hpmvs_engine_download_depth(hpmvs_engine_t* e, int cam, int level, float* out, int* rows, int* cols) {
+    if (!e || cam < 0 || cam >= e->ncams || level < 0 || level > e->opt.maxlevel || !rows || !cols) return HPMVS_E_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    HP_CUDA(cudaSetDevice(e->device));
+    int rc = ensure_depths(e); if (rc) return rc;
+    *rows = (int)(e->h_cams[cam].h[level] / 2.0); *cols = (int)(e->h_cams[cam].w[level] / 2.0);
+    if (out) HP_CUDA(cudaMemcpy(out, e->depths[cam][level], sizeof(float) * (size_t)(*rows) * (*cols), cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -150,4 +150,30 @@ int hpmvs_seed_patches(const hpmvs_options_t* opt, int ncams, const hpmvs_camera
     return 0;
 }
 
+int hpmvs_expand_candidates(int ncams, const hpmvs_camera_t* cams, int n, const hpmvs_patch_t* parents, const float* widths,
+                            int mode, hpmvs_patch_t* out) {
+    if (!cams || ncams <= 0 || n < 0 || (n > 0 && (!parents || !widths || !out)) || (mode != 4 && mode != 6)) return HPMVS_E_ARG;
+    for (int i = 0; i < n; i++) {
+        const hpmvs_patch_t& p = parents[i];
+        if (p.nimages <= 0 || p.images[0] < 0 || p.images[0] >= ncams) return HPMVS_E_ARG;
+        const hpmvs_camera_t& rc = cams[p.images[0]];
+        const Vec3 nrm{p.normal[0], p.normal[1], p.normal[2]};
+        const Vec3 ya = unit(cross(nrm, Vec3{rc.xaxis[0], rc.xaxis[1], rc.xaxis[2]}));
+        const Vec3 xa = cross(ya, nrm);
+        const float width = widths[i];
+        const float extend = (mode == 6) ? width : (float)(width / 4.0);
+        for (int ii = 0; ii < mode; ii++) {
+            const float angle = (mode == 6) ? (float)(2.0 * M_PI / mode * ii) : (float)(2.0 * M_PI / mode * ii + M_PI / 4);
+            const float dx = (float)cos((double)angle), dy = (float)sin((double)angle);
+            hpmvs_patch_t q = p;
+            q.center[0] = p.center[0] + (dx * xa.x + dy * ya.x) * extend;
+            q.center[1] = p.center[1] + (dx * xa.y + dy * ya.y) * extend;
+            q.center[2] = p.center[2] + (dx * xa.z + dy * ya.z) * extend;
+            q.scale = (mode == 6) ? (float)(width * 0.9 / 2.0) : (float)(width * 0.45 / 2.0);
+            out[(size_t)mode * i + ii] = q;
+        }
+    }
+    return 0;
+}
+
 }  // extern "C"

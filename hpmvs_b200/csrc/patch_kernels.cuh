@@ -60,6 +60,8 @@ struct DevCamera {
     int w[HPMVS_LEVELS], h[HPMVS_LEVELS];
     int pitch[HPMVS_LEVELS];              // row pitch in pixels (uchar4)
     const uchar4* img[HPMVS_LEVELS];
+    float* depth[HPMVS_LEVELS];           // Scene::m_depths[cam][level] (Scene.h:75-76), rows x cols, row-major
+    int drows[HPMVS_LEVELS], dcols[HPMVS_LEVELS];
 };
 
 struct KParams {
@@ -1057,6 +1059,137 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) ncc_kernel(const KParams
         __syncwarp();
     }
     if (lane == 0 && c_tex) atomicAdd(&K.counters[3], c_tex);
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// K5 ("next" row f-2): depth-map bookkeeping and the acceptance tests that follow optimize() in
+// CellProcessor::extend (src/hpmvs/CellProcessor.cpp:134-142, 197-201): Scene::setDepths (Scene.cpp:351-381),
+// depthTests / depthTest (:518-585), pixelFreeTests (:587-611), viewBlockTest (:613-644).
+// ----------------------------------------------------------------------------------------------------------
+constexpr float MAX_DEPTH = 1000.0f;      // Scene.cpp:33
+
+__global__ void depth_fill_kernel(float* p, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = MAX_DEPTH;
+}
+
+// Camera::mult (Camera.h:76-78)
+__device__ __forceinline__ f3 mult_pt(const DevCamera& cam, f4 X, int level) {
+    const float* p = cam.P[level];
+    return f3{(p[0] * X.x + p[1] * X.y) + (p[2] * X.z + p[3] * X.w), (p[4] * X.x + p[5] * X.y) + (p[6] * X.z + p[7] * X.w),
+              (p[8] * X.x + p[9] * X.y) + (p[10] * X.z + p[11] * X.w)};
+}
+// (int)(a / b + 0.5): f32 quotient, f64 addition, truncation
+__device__ __forceinline__ int round_px(float a, float b) { return (int)((double)(a / b) + 0.5); }
+// integer pixel / DEPTH_SUBSAMPLE (a double 2): f64 quotient, truncation
+__device__ __forceinline__ int sub2(int v) { return (int)((double)v / 2.0); }
+
+// setDepths(patch, false) for every (patch, view) pair; the reference's "d < old -> old = d" is an atomic float min
+__global__ void depth_set_kernel(const KParams K, const hpmvs_patch_t* __restrict__ patches, int n) {
+    const int total = n * MAXV;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const hpmvs_patch_t& p = patches[t / MAXV];
+        const int k = t % MAXV;
+        if (p.status != HPMVS_OK || k >= p.nimages) continue;
+        const int idx = p.images[k];
+        const DevCamera& cam = K.cams[idx];
+        const f4 c = ld4(p.center);
+        const f4 dd = sub4(c, ld4(cam.center));
+        const float fz = sqrtf(dot4(dd, dd));
+        const int level = leveli_from(cam, fz, p.scale, cam.nlevels - 1);
+        const f3 imgC = mult_pt(cam, c, level);
+        const int x = sub2(round_px(imgC.x, imgC.z)), y = sub2(round_px(imgC.y, imgC.z));
+        const float d = imgC.z;
+        if (!(d >= 0.0f)) continue;
+        if (x < 0 || x >= cam.dcols[level] || y < 0 || y >= cam.drows[level]) continue;
+        atomicMin(reinterpret_cast<int*>(cam.depth[level] + (size_t)y * cam.dcols[level] + x), __float_as_int(d));
+    }
+}
+
+__device__ __forceinline__ float full_depth(const DevCamera& cam, int xx, int yy) {
+    float depth = MAX_DEPTH;
+    int x = sub2(xx), y = sub2(yy);
+    for (int level = 0; level < cam.nlevels; level++) {
+        if (x < 0 || x >= cam.dcols[level] || y < 0 || y >= cam.drows[level]) return depth;
+        depth = fminf(depth, cam.depth[level][(size_t)y * cam.dcols[level] + x]);
+        x /= 2; y /= 2;
+    }
+    return depth;
+}
+
+// Scene::depthTest with neighbours = true (Scene.cpp:534-585); `abs(diff)` is the C int abs (quirk Q18)
+__device__ __forceinline__ bool depth_test(const DevCamera& cam, f4 c, f4 nrm, float scale, float margin, bool viewBlock) {
+    const f3 imgC = mult_pt(cam, c, 0);
+    const int ix0 = round_px(imgC.x, imgC.z) - 1, iy0 = round_px(imgC.y, imgC.z) - 1;
+    const float depth = imgC.z;
+    const f4 ray = normalized4(sub4(c, ld4(cam.center)));
+    const float factor = fminf(2.0f, 2.0f + dot4(ray, nrm));
+    const double thr = (double)(scale * margin * factor) * 2.0;
+    for (int yy = 0; yy < 3; yy++)
+        for (int xx = 0; xx < 3; xx++) {
+            const int ix = ix0 + xx, iy = iy0 + yy;
+            if (depth < 0.0f || ix < 0 || ix >= cam.w[0] || iy < 0 || iy >= cam.h[0]) return false;
+            const float imgDepth = full_depth(cam, ix, iy);
+            if (imgDepth >= MAX_DEPTH) { if (viewBlock) return false; else continue; }
+            const float diff = imgDepth - depth;
+            if (!viewBlock) { if (!((double)abs((int)diff) < thr)) return false; }
+            else { if (!((double)diff > thr)) return false; }
+        }
+    return true;
+}
+
+// one warp per patch: out[3*i] = depthTests, [3*i+1] = viewBlockTest, [3*i+2] = pixelFreeTests
+__global__ void accept_kernel(const KParams K, const hpmvs_patch_t* __restrict__ patches, int n, float margin, int* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int pi = warp; pi < n; pi += nwarps) {
+        const hpmvs_patch_t& p = patches[pi];
+        const f4 c = ld4(p.center), nrm = ld4(p.normal);
+        const float scale = p.scale;
+        const int nimg = min(max(p.nimages, 0), MAXV);
+        bool vis = false, fre = false;
+        if (lane < nimg) {
+            const DevCamera& cam = K.cams[p.images[lane]];
+            vis = depth_test(cam, c, nrm, scale, margin, false);
+            // pixelFreeTest (Scene.cpp:595-611)
+            const f4 dd = sub4(c, ld4(cam.center));
+            const int level = (int)roundf(level_from(cam, sqrtf(dot4(dd, dd)), scale));
+            if (level >= 0 && level < cam.nlevels) {
+                float u, v;
+                project(cam, c, level, u, v);
+                // project() already divided: imgC[2] is 1 (or -1 behind the camera)
+                float w = 1.0f;
+                const float* pr = cam.P[level];
+                if ((pr[8] * c.x + pr[9] * c.y) + (pr[10] * c.z + pr[11] * c.w) <= 0.0f) w = -1.0f;
+                const int ix = round_px(u, w), iy = round_px(v, w);
+                if (ix >= 0 && ix < cam.w[level] && iy >= 0 && iy < cam.h[level]) {
+                    const int x = sub2(ix), y = sub2(iy);
+                    float dm = MAX_DEPTH;
+                    if (x >= 0 && x < cam.dcols[level] && y >= 0 && y < cam.drows[level]) dm = cam.depth[level][(size_t)y * cam.dcols[level] + x];
+                    fre = (dm == MAX_DEPTH);
+                }
+            }
+        }
+        const int nvis = __popc(__ballot_sync(FULL, vis)), nfree = __popc(__ballot_sync(FULL, fre));
+        int nblock = 0;
+        for (int base = 0; base < K.ncams; base += 32) {
+            const int img = base + lane;
+            bool blk = false;
+            if (img < K.ncams) {
+                const DevCamera& cam = K.cams[img];
+                const f4 dd = sub4(c, ld4(cam.center));
+                const int level = (int)roundf(level_from(cam, sqrtf(dot4(dd, dd)), scale));
+                if (level >= 0 && level <= cam.nlevels - 1) {
+                    float u, v;
+                    project(cam, c, level, u, v);
+                    if (!(u < 0.0f || u > (float)cam.w[level] || v < 0.0f || v > (float)cam.h[level]))
+                        blk = depth_test(cam, c, nrm, scale, margin, true);
+                }
+            }
+            nblock += __popc(__ballot_sync(FULL, blk));
+        }
+        if (lane == 0) { out[3 * pi] = nvis; out[3 * pi + 1] = nblock; out[3 * pi + 2] = nfree; }
+    }
 }
 
 // ----------------------------------------------------------------------------------------------------------

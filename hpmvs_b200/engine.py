@@ -76,6 +76,11 @@ def _lib():
         L.hpmvs_error_string.argtypes = [C.c_int]; L.hpmvs_error_string.restype = C.c_char_p
         L.hpmvs_camera_from_nvm.argtypes = [C.c_double, dp, dp, C.c_int, C.c_int, C.c_int, C.POINTER(Camera)]
         L.hpmvs_extract_covis.argtypes = [C.c_int, C.c_int, ip, ip, C.c_int, ip, ip, C.c_int]
+        L.hpmvs_engine_depth_reset.argtypes = [vp]
+        L.hpmvs_depth_set_batch.argtypes = [vp, C.c_int, vp, vp]
+        L.hpmvs_accept_batch.argtypes = [vp, C.c_int, vp, C.c_float, ip, vp]
+        L.hpmvs_engine_download_depth.argtypes = [vp, C.c_int, C.c_int, fp, ip, ip]
+        L.hpmvs_expand_candidates.argtypes = [C.c_int, C.POINTER(Camera), C.c_int, vp, fp, C.c_int, vp]
         L.hpmvs_seed_patches.argtypes = [C.POINTER(Options), C.c_int, C.POINTER(Camera), C.c_int, dp, ip, ip, vp, u8p]
         _sigs_done = True
     return L
@@ -125,6 +130,16 @@ def seed_patches(options: Options, cameras: Sequence[Camera], xyz: np.ndarray, m
     _check(_lib().hpmvs_seed_patches(C.byref(options), len(cameras), cams, n, _p(xyz, C.c_double), _p(mo, C.c_int32),
                                      _p(mc, C.c_int32), out.ctypes.data, _p(valid, C.c_uint8)))
     return out, valid.astype(bool)
+
+
+def expand_candidates(cameras: Sequence[Camera], parents: np.ndarray, widths: np.ndarray, mode: int) -> np.ndarray:
+    """Candidates of CellProcessor::extend (mode 6) / ::branch (mode 4) (CellProcessor.cpp:98-119, 227-249)."""
+    cams = (Camera * len(cameras))(*cameras)
+    p = np.ascontiguousarray(parents); w = np.ascontiguousarray(widths, np.float32)
+    assert p.dtype == PATCH_DTYPE
+    out = np.zeros(len(p) * mode, PATCH_DTYPE)
+    _check(_lib().hpmvs_expand_candidates(len(cameras), cams, len(p), p.ctypes.data, _p(w, C.c_float), mode, out.ctypes.data))
+    return out
 
 
 # ---------------------------------------------------------------------------------------------- the engine
@@ -211,6 +226,29 @@ class Engine:
         assert patches.dtype == PATCH_DTYPE and patches.flags.c_contiguous
         out = np.zeros((len(patches), MAX_VIEWS), np.float32)
         _check(_lib().hpmvs_ncc_batch(self._h, len(patches), patches.ctypes.data, ref_idx, 1 if robust else 0, _p(out, C.c_float), None))
+        return out
+
+    # -- "next" rows: depth maps + acceptance tests --------------------------------------------
+    def depth_reset(self) -> None:
+        _check(_lib().hpmvs_engine_depth_reset(self._h))
+
+    def depth_set(self, patches: np.ndarray) -> None:
+        """n x Scene::setDepths(patch, false) for the records with status OK."""
+        assert patches.dtype == PATCH_DTYPE and patches.flags.c_contiguous
+        _check(_lib().hpmvs_depth_set_batch(self._h, len(patches), patches.ctypes.data, None))
+
+    def accept(self, patches: np.ndarray, margin: float = 1.0) -> np.ndarray:
+        """[n,3] = depthTests, viewBlockTest, pixelFreeTests per patch (Scene.cpp:518-644)."""
+        assert patches.dtype == PATCH_DTYPE and patches.flags.c_contiguous
+        out = np.zeros((len(patches), 3), np.int32)
+        _check(_lib().hpmvs_accept_batch(self._h, len(patches), patches.ctypes.data, float(margin), _p(out, C.c_int32), None))
+        return out
+
+    def download_depth(self, cam: int, level: int) -> np.ndarray:
+        r, c = C.c_int32(), C.c_int32()
+        _check(_lib().hpmvs_engine_download_depth(self._h, cam, level, None, C.byref(r), C.byref(c)))
+        out = np.zeros((r.value, c.value), np.float32)
+        _check(_lib().hpmvs_engine_download_depth(self._h, cam, level, _p(out, C.c_float), C.byref(r), C.byref(c)))
         return out
 
     def counters(self, reset: bool = False) -> Counters:

@@ -141,6 +141,24 @@ int  hpmvs_optimize_batch_device(hpmvs_engine_t *e, int n, const hpmvs_patch_t *
 int  hpmvs_ncc_batch(hpmvs_engine_t *e, int n, const hpmvs_patch_t *in, int ref_idx, int robust, float *inccs,
                      void *stream);
 
+/* ---- "next" rows: what CellProcessor::extend / branch do right around optimize() ---------------------------------- */
+
+/* Replaces the depth-map allocation in Scene::addCameras (src/hpmvs/Scene.cpp:74-81): (re)creates every
+ * (view, level) depth map at MAX_DEPTH = 1000.  Call after the cameras are set. */
+int  hpmvs_engine_depth_reset(hpmvs_engine_t *e);
+/* Replaces n calls of Scene::setDepths(patch, false) (Scene.cpp:351-381) for the records with status == HPMVS_OK;
+ * the "smaller depth wins" update is an atomic float min on the device. */
+int  hpmvs_depth_set_batch(hpmvs_engine_t *e, int n, const hpmvs_patch_t *patches, void *stream);
+/* Replaces, per patch, Scene::depthTests / viewBlockTest / pixelFreeTests (Scene.cpp:518-644) as used by
+ * CellProcessor::extend (src/hpmvs/CellProcessor.cpp:134-142): out[3*i+0..2] = the three counts. */
+int  hpmvs_accept_batch(hpmvs_engine_t *e, int n, const hpmvs_patch_t *patches, float margin, int32_t *out, void *stream);
+/* Reads one depth map back (rows x cols f32, row-major); out may be NULL to query the size. */
+int  hpmvs_engine_download_depth(hpmvs_engine_t *e, int cam, int level, float *out, int *rows, int *cols);
+/* Replaces the candidate construction of CellProcessor::extend (mode 6, CellProcessor.cpp:98-119) and ::branch
+ * (mode 4, :227-249) for n parent patches in cells of width widths[i]; out receives mode*n records. Host function. */
+int  hpmvs_expand_candidates(int ncams, const hpmvs_camera_t *cams, int n, const hpmvs_patch_t *parents,
+                             const float *widths, int mode, hpmvs_patch_t *out);
+
 /* ---- host-side scene surface (plain C++ on the host, no GPU needed): what feeds the engine ---- */
 
 /* Replaces mo3d::Camera::init (src/hpmvs/Camera.cpp:34-81) for one NVM camera line

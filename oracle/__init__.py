@@ -95,6 +95,11 @@ def lib():
         L.orc_objective.restype = C.c_double; L.orc_objective.argtypes = [vp, C.c_void_p, dp]
         L.orc_patch_color.argtypes = [vp, C.c_void_p, fp]
         L.orc_set_cr_asinf.argtypes = [C.c_int]
+        L.orc_depth_reset.argtypes = [vp]
+        L.orc_depth_set_batch.argtypes = [vp, C.c_int, C.c_void_p]
+        L.orc_get_depth.restype = C.POINTER(C.c_float); L.orc_get_depth.argtypes = [vp, C.c_int, C.c_int, ip, ip]
+        L.orc_accept_batch.argtypes = [vp, C.c_int, C.c_void_p, C.c_float, ip]
+        L.orc_expand_candidates.argtypes = [vp, C.c_int, C.c_void_p, fp, C.c_int, C.c_void_p]
         L.orc_testfunc_eval.restype = C.c_double; L.orc_testfunc_eval.argtypes = [C.c_int, dp]
         L.orc_bobyqa_testfunc.argtypes = [C.c_int, dp, dp, dp, C.c_double, C.c_int, dp, dp, dp, dp, C.c_int, ip]
         _lib = L
@@ -200,6 +205,31 @@ class OracleScene:
         p = np.ascontiguousarray(patch.reshape(1).copy())
         xa = np.asarray(x, np.float64)
         return lib().orc_objective(self._h, p.ctypes.data, _p(xa, C.c_double))
+
+    # -- "next" rows ------------------------------------------------------------------------
+    def depth_reset(self) -> None:
+        lib().orc_depth_reset(self._h)
+
+    def depth_set(self, patches: np.ndarray) -> None:
+        p = np.ascontiguousarray(patches)
+        lib().orc_depth_set_batch(self._h, len(p), p.ctypes.data)
+
+    def depth(self, cam: int, level: int) -> np.ndarray:
+        r, c = C.c_int32(), C.c_int32()
+        ptr = lib().orc_get_depth(self._h, cam, level, C.byref(r), C.byref(c))
+        return np.ctypeslib.as_array(ptr, shape=(r.value, c.value)).copy()
+
+    def accept(self, patches: np.ndarray, margin: float = 1.0) -> np.ndarray:
+        p = np.ascontiguousarray(patches)
+        out = np.zeros((len(p), 3), np.int32)
+        lib().orc_accept_batch(self._h, len(p), p.ctypes.data, float(margin), _p(out, C.c_int32))
+        return out
+
+    def expand_candidates(self, parents: np.ndarray, widths: np.ndarray, mode: int) -> np.ndarray:
+        p = np.ascontiguousarray(parents); w = np.ascontiguousarray(widths, np.float32)
+        out = np.zeros(len(p) * mode, PATCH_DTYPE)
+        lib().orc_expand_candidates(self._h, len(p), p.ctypes.data, _p(w, C.c_float), mode, out.ctypes.data)
+        return out
 
     def patch_color(self, patch: np.ndarray) -> np.ndarray:
         p = np.ascontiguousarray(patch.reshape(1).copy())

@@ -87,12 +87,18 @@ struct Image {
     std::vector<uint8_t> lvl[ORC_LEVELS];  // interleaved RGB, row stride 3*w (Image.cpp:62-63)
 };
 
+struct DepthMap { int rows = 0, cols = 0; std::vector<float> d; };   // Scene::m_depths[cam][level] (Scene.h:75-76)
+
 struct Scene {
     orc_options_t opt;
     std::vector<Camera> cameras;
     std::vector<Image> images;
     std::vector<std::vector<int>> covis;
+    std::vector<std::vector<DepthMap>> depths;
 };
+
+const float MAX_DEPTH = 1000.0f;        // Scene.cpp:33
+const double DEPTH_SUBSAMPLE = 2;       // Scene.h:78 (a double: integer pixel coordinates are divided in f64, then truncated)
 
 // Camera::init, src/hpmvs/Camera.cpp:34-81
 void camera_init(Camera& cam, double f, const double q[4], const double c[3], int width, int height, int maxLevel) {
@@ -611,6 +617,148 @@ V3 patch_color(const Scene& s, const V4& center, float scale, const int* images,
     return colors[colors.size() / 2];
 }
 
+// Camera::mult (Camera.h:76-78): projection without the perspective divide
+inline V3 mult(const Camera& cam, const V4& X, int level) {
+    V3 r;
+    for (int i = 0; i < 3; i++) {
+        const float* p = cam.P[level][i];
+        r[i] = (p[0] * X[0] + p[1] * X[1]) + (p[2] * X[2] + p[3] * X[3]);
+    }
+    return r;
+}
+
+// Scene::addCameras depth-map allocation (Scene.cpp:74-81)
+void alloc_depths(Scene& s) {
+    s.depths.assign(s.cameras.size(), {});
+    for (size_t c = 0; c < s.cameras.size(); c++) {
+        s.depths[c].resize(s.cameras[c].nlevels);
+        for (int l = 0; l < s.cameras[c].nlevels; l++) {
+            DepthMap& m = s.depths[c][l];
+            m.rows = (int)(s.images[c].h[l] / DEPTH_SUBSAMPLE);
+            m.cols = (int)(s.images[c].w[l] / DEPTH_SUBSAMPLE);
+            m.d.assign((size_t)m.rows * m.cols, MAX_DEPTH);
+        }
+    }
+}
+
+// Scene::setDepths(patch, false) (Scene.cpp:351-381)
+void set_depths(Scene& s, const orc_patch_t& p) {
+    const V4 c{{p.center[0], p.center[1], p.center[2], p.center[3]}};
+    for (int k = 0; k < p.nimages; k++) {
+        const int idx = p.images[k];
+        const Camera& cam = s.cameras[idx];
+        const int level = get_leveli(cam, c, p.scale, cam.nlevels - 1);
+        const V3 imgC = mult(cam, c, level);
+        const int x = (int)((int)(imgC[0] / imgC[2] + 0.5) / DEPTH_SUBSAMPLE);
+        const int y = (int)((int)(imgC[1] / imgC[2] + 0.5) / DEPTH_SUBSAMPLE);
+        const float d = imgC[2];
+        if (!(d >= 0)) continue;              // the reference CHECK-aborts here (Scene.cpp:363)
+        DepthMap& m = s.depths[idx][level];
+        if (x < 0 || x >= m.cols || y < 0 || y >= m.rows) continue;
+        float& old = m.d[(size_t)y * m.cols + x];
+        if (d < old) old = d;
+    }
+}
+
+// Scene::getFullDepth (Scene.cpp:404-432)
+float get_full_depth(const Scene& s, int img, int xx, int yy) {
+    float depth = MAX_DEPTH;
+    int x = (int)(xx / DEPTH_SUBSAMPLE), y = (int)(yy / DEPTH_SUBSAMPLE);
+    const int levels = s.cameras[img].nlevels;
+    for (int level = 0; level < levels; level++) {
+        const DepthMap& m = s.depths[img][level];
+        if (x < 0 || x >= m.cols || y < 0 || y >= m.rows) return depth;
+        depth = std::min(depth, m.d[(size_t)y * m.cols + x]);
+        x /= 2; y /= 2;
+    }
+    return depth;
+}
+
+// Scene::getDetphAtLevel (Scene.cpp:383-402)
+float get_depth_at_level(const Scene& s, int img, int xx, int yy, int level) {
+    const int x = (int)(xx / DEPTH_SUBSAMPLE), y = (int)(yy / DEPTH_SUBSAMPLE);
+    const DepthMap& m = s.depths[img][level];
+    if (x < 0 || x >= m.cols || y < 0 || y >= m.rows) return MAX_DEPTH;
+    return m.d[(size_t)y * m.cols + x];
+}
+
+// Scene::depthTest(patch, ix, iy, depth, image, margin, viewBlock) (Scene.cpp:558-585).
+// NOTE `abs(diff)` there is the C library's int abs(int): Scene.cpp only sees <cmath>/<cstdlib> declarations, so the
+// float argument is truncated to int first (quirk Q18; checked with g++ 13 on the same include set).
+bool depth_test_px(const Scene& s, const orc_patch_t& p, int ix, int iy, float depth, int image, float margin, bool viewBlock) {
+    if (depth < 0 || ix < 0 || ix >= s.images[image].w[0] || iy < 0 || iy >= s.images[image].h[0]) return false;
+    const float imgDepth = get_full_depth(s, image, ix, iy);
+    if (imgDepth >= MAX_DEPTH) return viewBlock ? false : true;
+    const V4 c{{p.center[0], p.center[1], p.center[2], p.center[3]}};
+    const V4 n{{p.normal[0], p.normal[1], p.normal[2], p.normal[3]}};
+    const V4 ray = normalized4(sub4(c, s.cameras[image].center));
+    const float diff = imgDepth - depth;
+    const float factor = std::min(2.0f, 2.0f + dot4(ray, n));
+    if (!viewBlock) return ::abs((int)diff) < p.scale * margin * factor * 2.0;
+    return diff > p.scale * margin * factor * 2.0;
+}
+
+// Scene::depthTest(patch, image, margin, neighbours=true, viewBlock) (Scene.cpp:534-556)
+bool depth_test(const Scene& s, const orc_patch_t& p, int image, float margin, bool viewBlock) {
+    const V4 c{{p.center[0], p.center[1], p.center[2], p.center[3]}};
+    const V3 imgC = mult(s.cameras[image], c, 0);
+    int ix = (int)(imgC[0] / imgC[2] + 0.5);
+    int iy = (int)(imgC[1] / imgC[2] + 0.5);
+    ix--; iy--;
+    for (int yy = 0; yy < 3; yy++)
+        for (int xx = 0; xx < 3; xx++)
+            if (!depth_test_px(s, p, ix + xx, iy + yy, imgC[2], image, margin, viewBlock)) return false;
+    return true;
+}
+
+// Scene::pixelFreeTest (Scene.cpp:595-611)
+bool pixel_free_test(const Scene& s, const orc_patch_t& p, int image) {
+    const V4 c{{p.center[0], p.center[1], p.center[2], p.center[3]}};
+    const Camera& cam = s.cameras[image];
+    const int level = (int)std::round(get_level(cam, c, p.scale));
+    if (level < 0 || level >= cam.nlevels) return false;
+    const V3 imgC = project(cam, c, level);
+    const int ix = (int)(imgC[0] / imgC[2] + 0.5), iy = (int)(imgC[1] / imgC[2] + 0.5);
+    if (ix < 0 || ix >= s.images[image].w[level] || iy < 0 || iy >= s.images[image].h[level]) return false;
+    return get_depth_at_level(s, image, ix, iy, level) == MAX_DEPTH;
+}
+
+// depthTests / viewBlockTest / pixelFreeTests (Scene.cpp:518-524, 613-644, 587-593)
+void acceptance_counts(const Scene& s, const orc_patch_t& p, float margin, int32_t out[3]) {
+    const V4 c{{p.center[0], p.center[1], p.center[2], p.center[3]}};
+    int nvis = 0, nblock = 0, nfree = 0;
+    for (int k = 0; k < p.nimages; k++) if (depth_test(s, p, p.images[k], margin, false)) ++nvis;
+    for (int img = 0; img < (int)s.images.size(); img++) {
+        const Camera& cam = s.cameras[img];
+        const int level = (int)std::round(get_level(cam, c, p.scale));
+        if (level < 0 || level > cam.nlevels - 1) continue;
+        const V3 imgC = project(cam, c, level);
+        if (imgC[0] < 0 || imgC[0] > s.images[img].w[level] || imgC[1] < 0 || imgC[1] > s.images[img].h[level]) continue;
+        if (depth_test(s, p, img, margin, true)) nblock++;
+    }
+    for (int k = 0; k < p.nimages; k++) if (pixel_free_test(s, p, p.images[k])) ++nfree;
+    out[0] = nvis; out[1] = nblock; out[2] = nfree;
+}
+
+// candidate construction of CellProcessor::extend (mode 6, CellProcessor.cpp:98-119) and ::branch (mode 4, :227-249)
+void expand_candidates(const Scene& s, const orc_patch_t& p, float width, int mode, orc_patch_t* out) {
+    const V3 n{{p.normal[0], p.normal[1], p.normal[2]}};
+    const V3 imgX = s.cameras[p.images[0]].xAxis;
+    const V3 yaxis = normalized3(cross3(n, imgX));
+    const V3 xaxis = cross3(yaxis, n);
+    const int N = mode;
+    const float extend = (mode == 6) ? width : (float)(width / 4.0);
+    for (int ii = 0; ii < N; ii++) {
+        const float angle = (mode == 6) ? (float)(2.0 * M_PI / N * ii) : (float)(2.0 * M_PI / N * ii + M_PI / 4);
+        const float dx = ::cos((double)angle);
+        const float dy = ::sin((double)angle);
+        orc_patch_t q = p;
+        for (int k = 0; k < 3; k++) q.center[k] = p.center[k] + (dx * xaxis[k] + dy * yaxis[k]) * extend;
+        q.scale = (mode == 6) ? (float)(width * 0.9 / 2.0) : (float)(width * 0.45 / 2.0);
+        out[ii] = q;
+    }
+}
+
 int optimize_one(const Scene& s, orc_patch_t& p) {
     PatchOptimizer po(&s);
     po.load(p);
@@ -878,6 +1026,28 @@ void orc_patch_color(void* scene, const orc_patch_t* patch, float rgb[3]) {
 }
 
 void orc_set_cr_asinf(int on) { g_cr_asinf = on; }
+
+void orc_depth_reset(void* scene) { alloc_depths(*static_cast<Scene*>(scene)); }
+void orc_depth_set_batch(void* scene, int n, const orc_patch_t* patches) {
+    Scene& s = *static_cast<Scene*>(scene);
+    if (s.depths.size() != s.cameras.size()) alloc_depths(s);
+    for (int i = 0; i < n; i++) if (patches[i].status == ORC_OK) set_depths(s, patches[i]);
+}
+const float* orc_get_depth(void* scene, int cam, int level, int* rows, int* cols) {
+    Scene& s = *static_cast<Scene*>(scene);
+    if (s.depths.size() != s.cameras.size()) alloc_depths(s);
+    *rows = s.depths[cam][level].rows; *cols = s.depths[cam][level].cols;
+    return s.depths[cam][level].d.data();
+}
+void orc_accept_batch(void* scene, int n, const orc_patch_t* patches, float margin, int32_t* out) {
+    Scene& s = *static_cast<Scene*>(scene);
+    if (s.depths.size() != s.cameras.size()) alloc_depths(s);
+    for (int i = 0; i < n; i++) acceptance_counts(s, patches[i], margin, out + 3 * i);
+}
+void orc_expand_candidates(void* scene, int n, const orc_patch_t* parents, const float* widths, int mode, orc_patch_t* out) {
+    const Scene& s = *static_cast<Scene*>(scene);
+    for (int i = 0; i < n; i++) expand_candidates(s, parents[i], widths[i], mode, out + (size_t)mode * i);
+}
 
 double orc_testfunc_eval(int func_id, const double x[3]) { return testfunc(func_id, x); }
 

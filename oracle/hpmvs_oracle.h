@@ -103,6 +103,15 @@ double orc_objective(void *scene, const orc_patch_t *patch, const double x[3]);
 /* Scene::getColor(const Patch3d&) (Scene.cpp:300-327) */
 void  orc_patch_color(void *scene, const orc_patch_t *patch, float rgb[3]);
 
+/* --- "next" rows: the steps right after optimize() in CellProcessor::extend (CellProcessor.cpp:134-142,197-201) --- */
+void  orc_depth_reset(void *scene);                                           /* Scene.cpp:74-81 */
+void  orc_depth_set_batch(void *scene, int n, const orc_patch_t *patches);    /* setDepths(p,false) for status==OK */
+const float *orc_get_depth(void *scene, int cam, int level, int *rows, int *cols);
+/* out[3*i+0..2] = depthTests, viewBlockTest, pixelFreeTests (Scene.cpp:518-644) */
+void  orc_accept_batch(void *scene, int n, const orc_patch_t *patches, float margin, int32_t *out);
+/* candidates of extend (mode 6) / branch (mode 4): CellProcessor.cpp:98-119, 227-249; out has mode*n records */
+void  orc_expand_candidates(void *scene, int n, const orc_patch_t *parents, const float *widths, int mode, orc_patch_t *out);
+
 /* 1: evaluate std::asin(float) of PatchOptimizer.cpp:427 correctly rounded instead of with this box's libm */
 void  orc_set_cr_asinf(int on);
 

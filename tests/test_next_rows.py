@@ -1,0 +1,71 @@
+"""Parity of the "next" rows around optimize(): candidate construction of CellProcessor::extend / branch
+(host, CPU test), Scene::setDepths and the acceptance tests depthTests / viewBlockTest / pixelFreeTests (GPU tests)."""
+import numpy as np
+import pytest
+
+import hpmvs_b200 as hp
+import oracle
+from helpers import small_plane, to_engine, to_oracle
+
+
+def test_expand_candidates_match_oracle_bit_for_bit():
+    sc, orc, seeds = small_plane()
+    cams = [hp.camera_from_nvm(c.f, c.q, c.c, img.shape[1], img.shape[0]) for c, img in zip(sc.cameras, sc.images)]
+    parents = seeds[:50]
+    widths = np.linspace(0.05, 0.4, 50).astype(np.float32)
+    for mode in (6, 4):
+        ref = orc.expand_candidates(parents, widths, mode)
+        got = hp.expand_candidates(cams, to_engine(parents), widths, mode)
+        assert len(got) == mode * 50
+        for f in ("center", "normal", "scale", "nimages"):
+            assert np.array_equal(ref[f], got[f]), (mode, f)
+        # geometry: candidates lie in the patch plane at the requested distance from the parent
+        d = got["center"][:, :3] - np.repeat(to_engine(parents)["center"][:, :3], mode, 0)
+        n = np.repeat(parents["normal"][:, :3], mode, 0)
+        assert np.abs((d * n).sum(1)).max() < 1e-5
+        r = np.linalg.norm(d, axis=1) / np.repeat(widths, mode)
+        assert np.allclose(r, 1.0 if mode == 6 else 0.25, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_depth_maps_and_acceptance_tests_bit_exact():
+    sc, orc, seeds = small_plane()
+    eng = hp.Engine.from_synth(sc)
+    oracle.set_cr_asinf(True)
+    try:
+        ref = orc.optimize_batch(seeds, nthreads=8)
+    finally:
+        oracle.set_cr_asinf(False)
+    got = eng.optimize(to_engine(seeds))
+    assert np.array_equal(ref["status"], got["status"])
+    ok = got["status"] == 0
+    # (1) empty depth maps: nothing is visible-tested away, every pixel is free
+    orc.depth_reset(); eng.depth_reset()
+    a_ref = orc.accept(ref, 1.0); a_got = eng.accept(got, 1.0)
+    assert np.array_equal(a_ref, a_got)
+    assert (a_got[ok][:, 1] == 0).all() and (a_got[ok][:, 2] == got["nimages"][ok]).all()
+    # (2) commit the first half of the optimized patches, then test all of them against that state
+    half = got.copy(); half_ref = ref.copy()
+    idx = np.nonzero(ok)[0]
+    drop = idx[len(idx) // 2:]
+    half["status"][drop] = 99; half_ref["status"][drop] = 99
+    orc.depth_set(half_ref); eng.depth_set(half)
+    for cam in range(len(sc.cameras)):
+        for lvl in range(6):
+            assert np.array_equal(orc.depth(cam, lvl), eng.download_depth(cam, lvl)), (cam, lvl)
+    assert any((eng.download_depth(0, l) < 1000.0).any() for l in range(6))
+    for margin in (1.0, 0.25):
+        a_ref = orc.accept(ref, margin); a_got = eng.accept(got, margin)
+        assert np.array_equal(a_ref, a_got), margin
+    # committed patches now see their own depth: fewer free pixels than before
+    assert a_got[idx[:len(idx) // 2], 2].sum() < got["nimages"][idx[:len(idx) // 2]].sum()
+    # (3) a patch pushed towards the cameras in front of the committed surface blocks views
+    front = got[ok][:40].copy(); front_ref = ref[ok][:40].copy()
+    front["center"][:, 2] -= 2.0; front_ref["center"][:, 2] -= 2.0
+    b_ref = orc.accept(front_ref, 1.0); b_got = eng.accept(front, 1.0)
+    assert np.array_equal(b_ref, b_got)
+    assert b_got[:, 1].max() >= 1
+    # idempotence: committing the same patches again changes nothing
+    before = [eng.download_depth(c, 4) for c in range(len(sc.cameras))]
+    eng.depth_set(half)
+    assert all(np.array_equal(b, eng.download_depth(c, 4)) for c, b in enumerate(before))
