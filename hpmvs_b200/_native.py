@@ -12,7 +12,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhpmvs_b200.so")
-SOURCES = [os.path.join(_HERE, "csrc", "engine.cu"), os.path.join(_HERE, "csrc", "host_scene.cpp")]
+SOURCES = [os.path.join(_HERE, "csrc", "engine.cu"), os.path.join(_HERE, "csrc", "host_scene.cpp"),
+           os.path.join(_HERE, "csrc", "host_io.cpp")]
 HEADERS = [os.path.join(_HERE, "csrc", "patch_kernels.cuh"), os.path.join(_HERE, "csrc", "bobyqa3.h"),
            os.path.join(_HERE, "..", "include", "hpmvs_b200.h")]
 

@@ -1,0 +1,192 @@
+// File formats on either side of the path ("next" row f-4), host C++ only:
+//   * NVM_V3 reader  - replaces mo3d::NVMReader::readFile (/root/reference/src/hpmvs/NVMReader.cpp:31-155)
+//   * ext-PLY writer - replaces DynOctTree::toExtPly      (/root/reference/include/hpmvs/doctree.h:525-622)
+//   * binary PPM (P6) level-0 image reader: the reference decodes JPEG through CImg/libjpeg (Image.cpp:46); this image
+//     has no JPEG decoder, so scenes carry PPM files instead (documented deviation).
+#include <ctype.h>
+#include <stdio.h>
+#include <string.h>
+#include <strings.h>
+
+#include <algorithm>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/hpmvs_b200.h"
+
+struct hpmvs_nvm {
+    struct Cam { std::string filename; double f, q[4], c[3], r; };
+    std::vector<Cam> cams;
+    std::vector<double> xyz, rgb, meas_xy;
+    std::vector<int32_t> offsets, meas_cam, meas_feat;
+    int n_models = 0;
+};
+
+namespace {
+std::string folder_of(const std::string& path) {
+    const size_t p = path.find_last_of('/');
+    return p == std::string::npos ? std::string("") : path.substr(0, p);
+}
+}  // namespace
+
+extern "C" {
+
+int hpmvs_nvm_open(const char* path, int fix_path, hpmvs_nvm_t** out) {
+    if (!path || !out) return HPMVS_E_ARG;
+    *out = nullptr;
+    std::ifstream in(path);
+    if (!in.good()) return HPMVS_E_ARG;
+    std::string header;
+    in >> header;
+    if (strcasecmp("NVM_V3", header.c_str()) != 0) return HPMVS_E_ARG;     // NVMReader.cpp:129
+    hpmvs_nvm* m = new hpmvs_nvm;
+    m->offsets.push_back(0);
+    const std::string folder = folder_of(path);
+    // models follow each other until one with 0 cameras (NVMReader.cpp:134-150); only models[0] is used
+    // downstream (src/main.cpp:112-116) but the stream must be consumed the same way
+    bool first = true;
+    while (in.good()) {
+        int ncam = 0;
+        if (!(in >> ncam) || ncam <= 0) break;
+        std::vector<hpmvs_nvm::Cam> cams(ncam);
+        for (auto& c : cams) {
+            int check = 0;
+            in >> c.filename >> c.f >> c.q[0] >> c.q[1] >> c.q[2] >> c.q[3] >> c.c[0] >> c.c[1] >> c.c[2] >> c.r >> check;
+            std::replace(c.filename.begin(), c.filename.end(), '"', ' ');            // NVMReader.cpp:73
+            if (fix_path && !c.filename.empty() && c.filename[0] != '/') c.filename = folder.empty() ? c.filename : folder + "/" + c.filename;
+        }
+        int npts = 0;
+        in >> npts;
+        m->n_models++;
+        for (int i = 0; i < npts; i++) {
+            double xyz[3], rgb[3];
+            int nm = 0;
+            in >> xyz[0] >> xyz[1] >> xyz[2] >> rgb[0] >> rgb[1] >> rgb[2] >> nm;
+            if (!in.good() && !in.eof()) { delete m; return HPMVS_E_ARG; }
+            for (int k = 0; k < nm; k++) {
+                int img = 0, feat = 0; double u = 0, v = 0;
+                in >> img >> feat >> u >> v;
+                if (first) { m->meas_cam.push_back(img); m->meas_feat.push_back(feat); m->meas_xy.push_back(u); m->meas_xy.push_back(v); }
+            }
+            if (first) {
+                m->xyz.insert(m->xyz.end(), xyz, xyz + 3); m->rgb.insert(m->rgb.end(), rgb, rgb + 3);
+                m->offsets.push_back((int32_t)m->meas_cam.size());
+            }
+        }
+        if (first) m->cams = cams;
+        first = false;
+    }
+    *out = m;
+    return 0;
+}
+
+void hpmvs_nvm_close(hpmvs_nvm_t* m) { delete m; }
+int hpmvs_nvm_num_models(const hpmvs_nvm_t* m) { return m ? m->n_models : 0; }
+int hpmvs_nvm_num_cameras(const hpmvs_nvm_t* m) { return m ? (int)m->cams.size() : 0; }
+int hpmvs_nvm_num_points(const hpmvs_nvm_t* m) { return m ? (int)m->offsets.size() - 1 : 0; }
+int hpmvs_nvm_num_measurements(const hpmvs_nvm_t* m) { return m ? (int)m->meas_cam.size() : 0; }
+
+int hpmvs_nvm_camera(const hpmvs_nvm_t* m, int i, char* filename, int cap, double* f, double q_wxyz[4], double c[3], double* r) {
+    if (!m || i < 0 || i >= (int)m->cams.size()) return HPMVS_E_ARG;
+    const auto& cam = m->cams[i];
+    if (filename && cap > 0) { strncpy(filename, cam.filename.c_str(), cap - 1); filename[cap - 1] = 0; }
+    if (f) *f = cam.f;
+    if (q_wxyz) memcpy(q_wxyz, cam.q, sizeof(cam.q));
+    if (c) memcpy(c, cam.c, sizeof(cam.c));
+    if (r) *r = cam.r;
+    return 0;
+}
+
+int hpmvs_nvm_points(const hpmvs_nvm_t* m, double* xyz, double* rgb, int32_t* offsets, int32_t* meas_cam, int32_t* meas_feat, double* meas_xy) {
+    if (!m) return HPMVS_E_ARG;
+    if (xyz) std::copy(m->xyz.begin(), m->xyz.end(), xyz);
+    if (rgb) std::copy(m->rgb.begin(), m->rgb.end(), rgb);
+    if (offsets) std::copy(m->offsets.begin(), m->offsets.end(), offsets);
+    if (meas_cam) std::copy(m->meas_cam.begin(), m->meas_cam.end(), meas_cam);
+    if (meas_feat) std::copy(m->meas_feat.begin(), m->meas_feat.end(), meas_feat);
+    if (meas_xy) std::copy(m->meas_xy.begin(), m->meas_xy.end(), meas_xy);
+    return 0;
+}
+
+// binary PPM; returns the size with rgb == NULL, fills rgb (3*w*h bytes, interleaved) otherwise
+int hpmvs_ppm_read(const char* path, int* width, int* height, uint8_t* rgb) {
+    if (!path || !width || !height) return HPMVS_E_ARG;
+    FILE* fh = fopen(path, "rb");
+    if (!fh) return HPMVS_E_ARG;
+    int vals[3], got = 0, c;
+    char magic[3] = {0, 0, 0};
+    if (fread(magic, 1, 2, fh) != 2 || magic[0] != 'P' || magic[1] != '6') { fclose(fh); return HPMVS_E_ARG; }
+    while (got < 3 && (c = fgetc(fh)) != EOF) {
+        if (c == '#') { while ((c = fgetc(fh)) != EOF && c != '\n') {} continue; }
+        if (isspace(c)) continue;
+        int v = 0;
+        while (c != EOF && isdigit(c)) { v = v * 10 + (c - '0'); c = fgetc(fh); }
+        vals[got++] = v;     // the single whitespace after maxval has just been consumed
+    }
+    if (got < 3 || vals[2] != 255 || vals[0] <= 0 || vals[1] <= 0) { fclose(fh); return HPMVS_E_ARG; }
+    *width = vals[0]; *height = vals[1];
+    int rc = 0;
+    if (rgb) {
+        const size_t n = (size_t)3 * vals[0] * vals[1];
+        if (fread(rgb, 1, n, fh) != n) rc = HPMVS_E_ARG;
+    }
+    fclose(fh);
+    return rc;
+}
+
+int hpmvs_ply_write_ext(const char* path, int n, const hpmvs_patch_t* p, int binary, int normal, int scale, int visibility) {
+    if (!path || n < 0 || (n > 0 && !p)) return HPMVS_E_ARG;
+    {
+        std::ofstream f(path, std::ofstream::out);
+        if (!f.good()) return HPMVS_E_ARG;
+        f << "ply" << std::endl;
+        if (binary) f << "format binary_little_endian 1.0" << std::endl;
+        else f << "format ascii 1.0" << std::endl;
+        f << "element vertex " << n << std::endl;
+        f << "property float x" << std::endl << "property float y" << std::endl << "property float z" << std::endl;
+        if (normal) f << "property float nx" << std::endl << "property float ny" << std::endl << "property float nz" << std::endl;
+        f << "property uchar red" << std::endl << "property uchar green" << std::endl << "property uchar blue" << std::endl;
+        if (scale) f << "property float scalar_scale" << std::endl;
+        if (visibility) {
+            f << "element point_visibility " << n << std::endl;
+            f << "property list uint uint visible_cameras" << std::endl;
+        }
+        f << "end_header" << std::endl;
+    }
+    std::ofstream d(path, binary ? std::ofstream::binary | std::ofstream::app : std::ofstream::app);
+    for (int i = 0; i < n; i++) {
+        const hpmvs_patch_t& q = p[i];
+        if (binary) {
+            d.write((const char*)q.center, 3 * sizeof(float));
+            if (normal) d.write((const char*)q.normal, 3 * sizeof(float));
+            const unsigned char c[3] = {(unsigned char)q.color[0], (unsigned char)q.color[1], (unsigned char)q.color[2]};
+            d.write((const char*)c, 3);
+            if (scale) d.write((const char*)&q.scale, sizeof(float));
+        } else {
+            d << q.center[0] << " " << q.center[1] << " " << q.center[2] << " ";
+            if (normal) d << q.normal[0] << " " << q.normal[1] << " " << q.normal[2] << " ";
+            d << (int)q.color[0] << " " << (int)q.color[1] << " " << (int)q.color[2] << " ";
+            if (scale) d << q.scale << " ";
+            d << std::endl;
+        }
+    }
+    if (visibility)
+        for (int i = 0; i < n; i++) {
+            const hpmvs_patch_t& q = p[i];
+            if (binary) {
+                const uint32_t k = (uint32_t)q.nimages;
+                d.write((const char*)&k, sizeof(uint32_t));
+                for (int j = 0; j < q.nimages; j++) { const uint32_t id = (uint32_t)q.images[j]; d.write((const char*)&id, sizeof(uint32_t)); }
+            } else {
+                d << (int)q.nimages << " ";
+                for (int j = 0; j < q.nimages; j++) d << (uint32_t)q.images[j] << " ";
+                d << std::endl;
+            }
+        }
+    d.flush();
+    return d.good() ? 0 : HPMVS_E_ARG;
+}
+
+}  // extern "C"

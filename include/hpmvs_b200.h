@@ -182,6 +182,29 @@ int  hpmvs_seed_patches(const hpmvs_options_t *opt, int ncams, const hpmvs_camer
                         const double *xyz, const int32_t *meas_offsets, const int32_t *meas_cam,
                         hpmvs_patch_t *out, uint8_t *valid);
 
+/* ---- file formats on either side of the path (host) ---------------------------------------------------------------- */
+
+typedef struct hpmvs_nvm hpmvs_nvm_t;
+/* Replaces mo3d::NVMReader::readFile (src/hpmvs/NVMReader.cpp:115-155): NVM_V3 text; cameras
+ * `file f qw qx qy qz cx cy cz r 0`, points `x y z r g b n (img feat u v)*n`; models are consumed until an empty
+ * one, model 0 is kept (src/main.cpp:112-116).  fix_path != 0 resolves relative image names against the NVM folder. */
+int  hpmvs_nvm_open(const char *path, int fix_path, hpmvs_nvm_t **out);
+void hpmvs_nvm_close(hpmvs_nvm_t *m);
+int  hpmvs_nvm_num_models(const hpmvs_nvm_t *m);
+int  hpmvs_nvm_num_cameras(const hpmvs_nvm_t *m);
+int  hpmvs_nvm_num_points(const hpmvs_nvm_t *m);
+int  hpmvs_nvm_num_measurements(const hpmvs_nvm_t *m);
+int  hpmvs_nvm_camera(const hpmvs_nvm_t *m, int i, char *filename, int cap, double *f, double q_wxyz[4], double c[3], double *r);
+/* any output pointer may be NULL; offsets has num_points+1 entries (CSR over the measurement arrays) */
+int  hpmvs_nvm_points(const hpmvs_nvm_t *m, double *xyz, double *rgb, int32_t *offsets, int32_t *meas_cam,
+                      int32_t *meas_feat, double *meas_xy);
+/* Level-0 image reader (binary PPM "P6", maxval 255); call with rgb == NULL to get the size first. */
+int  hpmvs_ppm_read(const char *path, int *width, int *height, uint8_t *rgb);
+/* Replaces DynOctTree::toExtPly (include/hpmvs/doctree.h:525-622): vertex element {x y z [nx ny nz] red green blue
+ * [scalar_scale]} + point_visibility element {list uint uint visible_cameras}; ascii or binary little endian. */
+int  hpmvs_ply_write_ext(const char *path, int n, const hpmvs_patch_t *patches, int binary, int normal, int scale,
+                         int visibility);
+
 int  hpmvs_engine_counters(hpmvs_engine_t *e, hpmvs_counters_t *out, int reset);
 /* The engine's own stream as a cudaStream_t, so callers can record events around asynchronous calls. */
 void *hpmvs_engine_stream(hpmvs_engine_t *e);
