@@ -80,6 +80,11 @@ struct hpmvs_engine {
     int blocks_per_sm = 0;
     int force_lanes = 0;
     int variant = 0;
+    int pvariant = 0;
+    int parked_mode = -1;            // -1 auto, 0 never, 1 always (HPMVS_PARKED)
+    hp::BqSlot* d_pool_bq = nullptr;
+    hp::LaneCtx* d_pool_ctx = nullptr;
+    int pool_ctas = 0;
     std::mutex mu;
 };
 
@@ -96,6 +101,18 @@ static const KernelVariant g_variants[] = {HP_VARIANT(2, 10, 32), HP_VARIANT(2, 
                                            HP_VARIANT(6, 10, 10), HP_VARIANT(1, 8, 32), HP_VARIANT(3, 10, 20), HP_VARIANT(3, 10, 23), HP_VARIANT(3, 10, 24),
                                            HP_VARIANT(3, 9, 24), HP_VARIANT(3, 12, 23), HP_VARIANT(2, 12, 32), HP_VARIANT(2, 14, 32)};
 static const int g_default_variant = 0;
+
+// parked-slot variant of the same kernel (patch state pools in HBM/L2): used when a batch has more patches than the
+// resident variant can keep in flight (64 per SM)
+struct ParkedVariant {
+    int ow, sw, lpw;
+    void (*fn)(const hp::KParams);
+    size_t smem;
+};
+#define HP_PVARIANT(OW, SW, LPW) {OW, SW, LPW, hp::optimize_kernel_parked<OW, SW, LPW>, sizeof(hp::CtaSharedP<OW, SW, LPW>)}
+static const ParkedVariant g_pvariants[] = {HP_PVARIANT(2, 10, 32), HP_PVARIANT(4, 10, 16), HP_PVARIANT(4, 12, 16), HP_PVARIANT(2, 12, 32),
+                                            HP_PVARIANT(3, 10, 21), HP_PVARIANT(3, 12, 20), HP_PVARIANT(4, 14, 12), HP_PVARIANT(6, 12, 10)};
+static const int g_default_pvariant = 0;
 
 static int ensure_patch_capacity(hpmvs_engine* e, size_t n) {
     if (n <= e->cap_patches) return 0;
@@ -207,6 +224,15 @@ int hpmvs_engine_create(const hpmvs_options_t* opt, int device, hpmvs_engine_t**
                                                           e->smem_bytes));
     if (e->blocks_per_sm < 1) e->blocks_per_sm = 1;
     if (const char* fl = getenv("HPMVS_FORCE_LANES")) e->force_lanes = atoi(fl);
+    if (const char* pk = getenv("HPMVS_PARKED")) e->parked_mode = atoi(pk);
+    e->pvariant = g_default_pvariant;
+    if (const char* cfg = getenv("HPMVS_PCONFIG")) {
+        int ow = 0, sw = 0, lpw = 0;
+        if (sscanf(cfg, "%d,%d,%d", &ow, &sw, &lpw) == 3)
+            for (size_t i = 0; i < sizeof(g_pvariants) / sizeof(g_pvariants[0]); i++)
+                if (g_pvariants[i].ow == ow && g_pvariants[i].sw == sw && g_pvariants[i].lpw == lpw) e->pvariant = (int)i;
+    }
+    HP_CUDA(cudaFuncSetAttribute(g_pvariants[e->pvariant].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_pvariants[e->pvariant].smem));
     *out = e;
     return 0;
 }
@@ -222,6 +248,7 @@ void hpmvs_engine_destroy(hpmvs_engine_t* e) {
         for (auto* d : cam)
             if (d) cudaFree(d);
     cudaFree(e->d_accept);
+    cudaFree(e->d_pool_bq); cudaFree(e->d_pool_ctx);
     cudaFree(e->d_cams); cudaFree(e->d_covis_off); cudaFree(e->d_covis_ids);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_inccs); cudaFree(e->d_stage);
     cudaFree(e->d_work); cudaFree(e->d_counters);
@@ -389,8 +416,32 @@ static int launch_optimize(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, hp
     if (lanes > V.lpw) lanes = V.lpw;
     if (e->force_lanes > 0) lanes = e->force_lanes;
     K.lanes_per_warp = lanes;
+    // more patches than resident slots -> parked variant (virtual slots per CTA, state pools in HBM/L2)
+    const bool parked = e->parked_mode == 1 || (e->parked_mode != 0 && (long long)n > (long long)e->sm_count * V.ow * V.lpw * 5 / 4);
     HP_CUDA(cudaEventRecord(e->ev0, s));
-    V.fn<<<grid, (V.ow + V.sw) * 32, e->smem_opt_bytes, s>>>(K);
+    if (!parked) {
+        V.fn<<<grid, (V.ow + V.sw) * 32, e->smem_opt_bytes, s>>>(K);
+    } else {
+        const ParkedVariant& PV = g_pvariants[e->pvariant];
+        const int g_parked_ow = PV.ow;
+        grid = e->sm_count;
+        if (e->pool_ctas < grid) {
+            cudaFree(e->d_pool_bq); cudaFree(e->d_pool_ctx);
+            e->d_pool_bq = nullptr; e->d_pool_ctx = nullptr; e->pool_ctas = 0;
+            HP_CUDA(cudaMalloc(&e->d_pool_bq, sizeof(hp::BqSlot) * (size_t)grid * hp::VMAX));
+            HP_CUDA(cudaMalloc(&e->d_pool_ctx, sizeof(hp::LaneCtx) * (size_t)grid * hp::VMAX));
+            e->pool_ctas = grid;
+        }
+        int v = (n + grid - 1) / grid;                          // virtual slots per CTA: all patches in flight if they fit
+        v = (v + g_parked_ow - 1) / g_parked_ow * g_parked_ow;
+        if (v > hp::VMAX) v = hp::VMAX;
+        if (v < g_parked_ow) v = g_parked_ow;
+        if (const char* vs = getenv("HPMVS_VSLOTS")) { v = atoi(vs) / g_parked_ow * g_parked_ow; if (v < g_parked_ow) v = g_parked_ow; if (v > hp::VMAX) v = hp::VMAX; }
+        K.vslots = v;
+        K.pool_bq = e->d_pool_bq;
+        K.pool_ctx = e->d_pool_ctx;
+        PV.fn<<<grid, (PV.ow + PV.sw) * 32, PV.smem, s>>>(K);
+    }
     HP_CUDA(cudaEventRecord(e->ev1, s));
     e->launches++;
     HP_CUDA(cudaGetLastError());

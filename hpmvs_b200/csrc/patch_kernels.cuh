@@ -80,6 +80,10 @@ struct KParams {
     int* work_counter;
     unsigned long long* counters;   // patches, ok, evals, textures
     int lanes_per_warp;             // patches kept in flight per warp (1..32)
+    // parked variant: per-CTA pools of virtual patch slots in HBM/L2 (state + context), `vslots` per CTA
+    struct BqSlot* pool_bq;
+    struct LaneCtx* pool_ctx;
+    int vslots;
 };
 
 struct ViewSetup {
@@ -873,21 +877,18 @@ __device__ __forceinline__ int q_pop(QueueShared& C, int lane) {
 }
 
 // FILL: fetch patches until one passes the pre-stage (-> ST_NEW) or the queue is empty (-> ST_DEAD)
-__device__ __noinline__ void serve_fill(LaneCtx& P, int* sstate_slot, Scratch& W, const KParams& K, int lane, unsigned long long* cnt) {
+// returns ST_NEW (P holds a patch that passed the pre-stage) or ST_DEAD (work queue empty)
+__device__ __noinline__ int serve_fill(LaneCtx& P, Scratch& W, const KParams& K, int lane, unsigned long long* cnt) {
     for (;;) {
         int pi = 0;
         if (lane == 0) pi = atomicAdd(K.work_counter, 1);
         pi = __shfl_sync(FULL, pi, 0);
-        if (pi >= K.n) {
-            if (lane == 0) st_state(sstate_slot, ST_DEAD);
-            return;
-        }
+        if (pi >= K.n) return ST_DEAD;
         load_patch(P, K.in[pi], pi, lane);
         const int st = pre_stage(W, P, K, lane);
         if (st == HPMVS_OK) {
             __syncwarp();
-            if (lane == 0) st_state(sstate_slot, ST_NEW);
-            return;
+            return ST_NEW;
         }
         retire_patch(W, P, K, lane, st);
         if (lane == 0) { cnt[0]++; cnt[3] += P.textures; }
@@ -1015,9 +1016,11 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
                 retire_patch(W, P, K, lane, st);
                 if (lane == 0) { cnt[0]++; cnt[1] += (st == HPMVS_OK); cnt[2] += P.evals; cnt[3] += P.textures; }
                 __syncwarp();
-                serve_fill(P, &C.sstate[slot], W, K, lane, cnt);
+                const int ns = serve_fill(P, W, K, lane, cnt);
+                if (lane == 0) st_state(&C.sstate[slot], ns);
             } else {   // REQ_FILL
-                serve_fill(P, &C.sstate[slot], W, K, lane, cnt);
+                const int ns = serve_fill(P, W, K, lane, cnt);
+                if (lane == 0) st_state(&C.sstate[slot], ns);
             }
             __syncwarp();
         }
@@ -1032,6 +1035,206 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
         }
 #endif
         (void)t_other;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// K2p: the same kernel with PARKED patch slots.  Shared memory caps the resident variant at 64 patches per SM
+// (1.6 KB of FP64 optimizer state each) and throughput = patches in flight / round latency.  Here every CTA owns
+// `vslots` (<= VMAX) virtual slots whose optimizer state and patch context live in an HBM/L2 pool; the shared-memory
+// slots are only staging buffers: an optimizer warp claims up to LPW READY slots, copies their state in (16-byte
+// vectors, L2-resident), advances them lane-parallel, copies them back and publishes the objective requests.  While
+// those wait for the samplers the warp is already advancing another batch, so it never idles as long as enough
+// patches are in flight.  Samplers work on a private shared-memory copy of the patch context.
+// ----------------------------------------------------------------------------------------------------------
+constexpr int VMAX = 256;
+constexpr int MIN_BATCH = 12;            // lanes worth starting an optimizer round for while objectives are still pending
+
+template <int OPT_WARPS, int SAMPLER_WARPS, int LPW>
+struct __align__(16) CtaSharedP {
+    BqSlot stage_bq[OPT_WARPS * LPW];
+    LaneCtx stage_ctx[OPT_WARPS * LPW];
+    int claim[OPT_WARPS][32];
+    double fval[VMAX];
+    int sstate[VMAX];
+    QueueShared Q;
+    struct Samp { Scratch S; LaneCtx P; } samp[SAMPLER_WARPS];
+};
+
+// warp-cooperative copies between the pool (global, read/written around L1) and shared memory, 16 bytes per lane
+// (8-byte granules: the padded optimizer slots are only 8-byte aligned)
+template <int BYTES>
+__device__ __forceinline__ void copy_in(void* smem, const void* gmem, int lane) {
+    static_assert(BYTES % 8 == 0, "8-byte granules");
+    const uint2* g = reinterpret_cast<const uint2*>(gmem);
+    uint2* s = reinterpret_cast<uint2*>(smem);
+#pragma unroll
+    for (int i = lane; i < BYTES / 8; i += 32) s[i] = __ldcg(g + i);
+}
+template <int BYTES>
+__device__ __forceinline__ void copy_out(void* gmem, const void* smem, int lane) {
+    static_assert(BYTES % 8 == 0, "8-byte granules");
+    uint2* g = reinterpret_cast<uint2*>(gmem);
+    const uint2* s = reinterpret_cast<const uint2*>(smem);
+#pragma unroll
+    for (int i = lane; i < BYTES / 8; i += 32) __stcg(g + i, s[i]);
+}
+constexpr int BQ_COPY_BYTES = (int)sizeof(bq3::State);
+static_assert(sizeof(bq3::State) % 8 == 0 && sizeof(LaneCtx) % 8 == 0, "pool copies in 8-byte granules");
+
+template <int OPT_WARPS, int SAMPLER_WARPS, int LPW>
+__global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_kernel_parked(const KParams K) {
+    using CtaShared = CtaSharedP<OPT_WARPS, SAMPLER_WARPS, LPW>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CtaShared& C = *reinterpret_cast<CtaShared*>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int V = K.vslots;                       // multiple of OPT_WARPS
+    BqSlot* pool_bq = K.pool_bq + (size_t)blockIdx.x * VMAX;
+    LaneCtx* pool_ctx = K.pool_ctx + (size_t)blockIdx.x * VMAX;
+
+    for (int i = threadIdx.x; i < QCAP; i += blockDim.x) C.Q.queue[i] = 0;
+    for (int i = threadIdx.x; i < VMAX; i += blockDim.x) C.sstate[i] = ST_DEAD;
+    if (threadIdx.x == 0) { C.Q.q_head = 0; C.Q.q_tail = 0; C.Q.opt_alive = OPT_WARPS; }
+    __syncthreads();
+
+    if (warp < OPT_WARPS) {
+        // =========================================== optimizer warp ===========================================
+        const int VW = V / OPT_WARPS, v0 = warp * VW;
+        for (int i = lane; i < VW; i += 32) { st_state(&C.sstate[v0 + i], ST_FILLING); q_push(C.Q, REQ_FILL, v0 + i); }
+        __syncwarp();
+        LaneCtx& mine = C.stage_ctx[warp * LPW + (lane < LPW ? lane : 0)];
+        bq3::State& bq = C.stage_bq[warp * LPW + (lane < LPW ? lane : 0)].s;
+        int tries = 0;
+        for (;;) {
+            // ---- claim up to LPW ready slots of this warp's range ---------------------------------------------
+            int count = 0, npend = 0, nlive = 0;
+            for (int base = 0; base < VW; base += 32) {
+                const int i = base + lane;
+                const int st = (i < VW) ? ld_state(&C.sstate[v0 + i]) : ST_DEAD;
+                const bool ready = (st == ST_EVAL_DONE || st == ST_NEW);
+                const unsigned m = __ballot_sync(FULL, ready);
+                const int pos = count + __popc(m & ((1u << lane) - 1u));
+                if (ready && pos < LPW) C.claim[warp][pos] = (v0 + i) | (st == ST_NEW ? 0x10000 : 0);
+                count = min(LPW, count + __popc(m));
+                npend += __popc(__ballot_sync(FULL, st == ST_EVAL_PENDING));
+                nlive += __popc(__ballot_sync(FULL, st != ST_DEAD));
+            }
+            __syncwarp();
+            if (count == 0) {
+                if (nlive == 0) break;
+                __nanosleep(200);
+                continue;
+            }
+            if (count < MIN_BATCH && npend > 0 && tries < 40) { ++tries; __nanosleep(500); continue; }
+            tries = 0;
+            __threadfence_block();
+            // ---- stage in: context always, optimizer state unless the patch is new -------------------------------
+            for (int j = 0; j < count; j++) {
+                const int e = C.claim[warp][j], slot = e & 0xffff;
+                copy_in<(int)sizeof(LaneCtx)>(&C.stage_ctx[warp * LPW + j], &pool_ctx[slot], lane);
+                if (!(e >> 16)) copy_in<BQ_COPY_BYTES>(&C.stage_bq[warp * LPW + j], &pool_bq[slot], lane);
+            }
+            __syncwarp();
+            // ---- advance lane-parallel ------------------------------------------------------------------------------
+            int st = 0, slot = 0;
+            if (lane < count) {
+                const int e = C.claim[warp][lane];
+                slot = e & 0xffff;
+                double xcur[3];
+                int act;
+                if (e >> 16) {
+                    const double lb[3] = {-HUGE_VAL, -23.99999, -23.99999};
+                    const double ub[3] = {HUGE_VAL, 23.99999, 23.99999};
+                    double x0[3];
+                    init_parameters(mine, K, lb, ub, x0);
+                    act = bq3::start(bq, x0, lb, ub, 1.e-7, 1000, xcur);
+                } else {
+                    const double f = *reinterpret_cast<volatile double*>(&C.fval[slot]);
+                    act = bq3::advance(bq, f, xcur);
+                }
+                if (act == bq3::ASK) { set_center_norm(mine, K, xcur); st = ST_EVAL_PENDING; }
+                else {
+                    st = ST_POSTING;
+                    const int rc = bq.rc;                      // optimizePatch's epilogue (:364-381)
+                    mine.nlopt_rc = rc; mine.evals = bq.nevals; mine.score = bq.minf;
+                    if (rc >= 1 && rc <= 4) {
+                        double xf[3];
+                        bq3::result_x(bq, xf);
+                        set_center_norm(mine, K, xf);
+                        mine.status = HPMVS_OK;
+                    } else {
+                        mine.status = rc == bq3::R_ROUNDOFF_LIMITED ? HPMVS_FAIL_OPT_ROUNDOFF
+                                      : rc == bq3::R_MAXEVAL_REACHED ? HPMVS_FAIL_OPT_MAXEVAL : HPMVS_FAIL_OPT_OTHER;
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- stage out and publish ------------------------------------------------------------------------------
+            for (int j = 0; j < count; j++) {
+                const int sl = C.claim[warp][j] & 0xffff;
+                copy_out<(int)sizeof(LaneCtx)>(&pool_ctx[sl], &C.stage_ctx[warp * LPW + j], lane);
+                copy_out<BQ_COPY_BYTES>(&pool_bq[sl], &C.stage_bq[warp * LPW + j], lane);
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane < count) {
+                st_state(&C.sstate[slot], st);
+                q_push(C.Q, st == ST_EVAL_PENDING ? REQ_EVAL : REQ_POST, slot);
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (atomicSub(&C.Q.opt_alive, 1) == 1)
+                for (int i = 0; i < SAMPLER_WARPS; i++) q_push(C.Q, REQ_EXIT, 0);
+        }
+    } else {
+        // ============================================ sampler warp ============================================
+        Scratch& W = C.samp[warp - OPT_WARPS].S;
+        LaneCtx& P = C.samp[warp - OPT_WARPS].P;
+        unsigned long long cnt[4] = {0, 0, 0, 0};
+        for (;;) {
+            const int e = q_pop(C.Q, lane);
+            const int kind = e >> 16, slot = e & 0xffff;
+            if (kind == REQ_EXIT) break;
+            int ns = -1;
+            if (kind == REQ_EVAL) {
+                copy_in<(int)sizeof(LaneCtx)>(&P, &pool_ctx[slot], lane);
+                __syncwarp();
+                const int tex0 = P.textures;
+                eval_dots(W, P, K, lane, 0, false, true);
+                const double f = objective_value(W, P, K, lane);
+                __syncwarp();
+                if (lane == 0) {
+                    if (P.textures != tex0) __stcg(&pool_ctx[slot].textures, P.textures);
+                    __threadfence();
+                    *reinterpret_cast<volatile double*>(&C.fval[slot]) = f;
+                    st_state(&C.sstate[slot], ST_EVAL_DONE);
+                }
+            } else {
+                if (kind == REQ_POST) {
+                    copy_in<(int)sizeof(LaneCtx)>(&P, &pool_ctx[slot], lane);
+                    __syncwarp();
+                    int st = P.status;
+                    if (st == HPMVS_OK) st = post_stage(W, P, K, lane);
+                    retire_patch(W, P, K, lane, st);
+                    if (lane == 0) { cnt[0]++; cnt[1] += (st == HPMVS_OK); cnt[2] += P.evals; cnt[3] += P.textures; }
+                    __syncwarp();
+                }
+                ns = serve_fill(P, W, K, lane, cnt);
+                __syncwarp();
+                if (ns == ST_NEW) copy_out<(int)sizeof(LaneCtx)>(&pool_ctx[slot], &P, lane);
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) st_state(&C.sstate[slot], ns);
+            }
+            __syncwarp();
+        }
+        if (lane == 0 && cnt[0]) {
+            atomicAdd(&K.counters[0], cnt[0]); atomicAdd(&K.counters[1], cnt[1]);
+            atomicAdd(&K.counters[2], cnt[2]); atomicAdd(&K.counters[3], cnt[3]);
+        }
     }
 }
 

@@ -156,3 +156,23 @@ def test_size_independent_properties_large_batch():
     assert ((a["nimages"][ok] >= 3) & (a["nimages"][ok] <= 8)).all()
     n = np.linalg.norm(a["normal"][ok][:, :3], axis=1)
     assert np.abs(n - 1).max() < 1e-5
+
+
+def test_parked_variant_bit_exact(plane, monkeypatch):
+    """Large batches run the parked-slot variant of the kernel (patch state pools in HBM/L2); force it on the small
+    scene and require the same bits as the resident variant and the oracle."""
+    sc, orc, seeds, eng = plane
+    monkeypatch.setenv("HPMVS_PARKED", "1")
+    monkeypatch.setenv("HPMVS_VSLOTS", "6")          # fewer virtual slots than patches per CTA: slots are recycled
+    eng_p = hp.Engine.from_synth(sc)
+    pe = to_engine(seeds)
+    a = eng.optimize(pe)
+    b = eng_p.optimize(pe)
+    assert a.tobytes() == b.tobytes()
+    oracle.set_cr_asinf(True)
+    try:
+        ref = orc.optimize_batch(seeds, nthreads=8)
+    finally:
+        oracle.set_cr_asinf(False)
+    st = compare_outputs(ref, b)
+    assert st["status_equal"] == st["n"] and st["bit_exact"] == st["both_ok"] and st["vis_equal"] == st["both_ok"]
