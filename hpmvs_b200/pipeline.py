@@ -1,0 +1,171 @@
+"""Level-synchronous host driver for the expand -> optimize -> filter loop around the engine.
+
+The reference's scheduler (CellProcessor + DynOctTree, /root/reference/src/hpmvs/CellProcessor.cpp:369-420) walks one
+priority queue per octree sub-tree and commits every accepted patch before it creates the next candidate.  That
+serial order cannot feed tens of thousands of patches to a GPU, and rebuilding the octree scheduler is out of scope
+(SURVEY section 8); this driver is the batching stand-in the survey asks for (section 7, "wavefront"): per tree level it
+collects the candidates of ALL cells, optimises them in one batch, runs the acceptance tests against a snapshot of
+the depth maps and then commits the survivors in a deterministic order.  It keeps the reference's per-cell rules:
+
+  * seeds:   reject if the optimised centre moved more than 2*scale (Scene.cpp:171), one patch per cell, the
+             best-supported patch wins (CellProcessor::filter, CellProcessor.cpp:43-82)
+  * extend:  6 candidates at one cell width, scale = width*0.9/2 (CellProcessor.cpp:98-119); accepted when
+             width/2 < 2*scale < width, drift < 1.5*width, depthTests >= MIN_IMAGES, viewBlockTest < MIN_IMAGES,
+             pixelFreeTests >= MIN_IMAGES-1 and > 75 % of the views (CellProcessor.cpp:129-142)
+  * branch:  4 candidates at width/4, scale = width*0.45/2, kept when they stay inside the parent cell
+             (CellProcessor.cpp:227-264); children live in cells of half the width
+
+It is written against a small backend protocol so that the SAME host logic runs on the GPU engine and on the CPU
+oracle - tests/test_pipeline.py requires identical patch sets from both.
+"""
+from __future__ import annotations
+
+import dataclasses
+import time
+from typing import Dict, List, Tuple
+
+import numpy as np
+
+MIN_IMAGES = 3
+DEPTH_TEST_FACTOR = 1.0
+
+
+class EngineBackend:
+    """The B200 engine (hpmvs_b200.Engine) behind the driver protocol."""
+
+    def __init__(self, engine):
+        from . import engine as E
+        self.e = engine
+        self.dtype = E.PATCH_DTYPE
+        self._expand = E.expand_candidates
+        self.e.depth_reset()
+
+    def optimize(self, rec): return self.e.optimize(np.ascontiguousarray(rec))
+    def accept(self, rec, margin): return self.e.accept(np.ascontiguousarray(rec), margin)
+    def depth_set(self, rec): self.e.depth_set(np.ascontiguousarray(rec))
+    def expand(self, parents, widths, mode): return self._expand(self.e.cameras, np.ascontiguousarray(parents), widths, mode)
+
+
+@dataclasses.dataclass
+class PipelineStats:
+    optimized_calls: int = 0
+    optimized_ok: int = 0
+    seconds_optimize: float = 0.0
+    seconds_accept: float = 0.0
+    per_level: List[Tuple[int, int, int]] = dataclasses.field(default_factory=list)   # (level, extended, branched)
+
+
+def _cell_keys(centers: np.ndarray, origin: np.ndarray, width: float) -> np.ndarray:
+    return np.floor((centers[:, :3].astype(np.float64) - origin) / width).astype(np.int64)
+
+
+def _pack(keys: np.ndarray) -> np.ndarray:
+    k = keys + (1 << 20)
+    return (k[:, 0] << 42) | (k[:, 1] << 21) | k[:, 2]
+
+
+class WavefrontDriver:
+    def __init__(self, backend, origin, root_width: float, start_level: int, final_level: int, max_rounds: int = 64):
+        self.b = backend
+        self.origin = np.asarray(origin, np.float64)
+        self.root_width = float(root_width)
+        self.start_level, self.final_level, self.max_rounds = start_level, final_level, max_rounds
+        self.stats = PipelineStats()
+
+    def width(self, level: int) -> float:
+        return self.root_width / (1 << level)
+
+    # -- helpers ------------------------------------------------------------------------------------------
+    def _optimize(self, rec):
+        t = time.perf_counter()
+        out = self.b.optimize(rec)
+        self.stats.seconds_optimize += time.perf_counter() - t
+        self.stats.optimized_calls += len(rec)
+        self.stats.optimized_ok += int((out["status"] == 0).sum())
+        return out
+
+    def _insert(self, level_cells: Dict[int, np.ndarray], rec: np.ndarray, width: float) -> np.ndarray:
+        """One patch per cell; on a collision the patch with more views wins (filter), then the earlier one.
+        Returns a mask of the records that now live in the grid."""
+        keys = _pack(_cell_keys(rec["center"], self.origin, width))
+        live = np.zeros(len(rec), bool)
+        for i, k in enumerate(keys.tolist()):
+            old = level_cells.get(k)
+            if old is None or rec["nimages"][i] > old["nimages"]:
+                level_cells[k] = rec[i].copy()
+                live[i] = True
+        return live
+
+    # -- the loop -----------------------------------------------------------------------------------------
+    def run(self, seeds: np.ndarray) -> np.ndarray:
+        out = self._optimize(seeds)
+        ok = out["status"] == 0
+        moved = np.linalg.norm(out["center"][:, :3] - seeds["center"][:, :3], axis=1)
+        ok &= ~(moved > out["scale"] * 2)                                    # Scene.cpp:171
+        cells: Dict[int, np.ndarray] = {}
+        level = self.start_level
+        first = out[ok]
+        self._insert(cells, first, self.width(level))
+        self.b.depth_set(np.array(list(cells.values()), dtype=self.b.dtype) if cells else first[:0])
+        final: List[np.ndarray] = []
+        while True:
+            w = self.width(level)
+            frontier = np.array(list(cells.values()), dtype=self.b.dtype) if cells else first[:0]
+            n_ext = 0
+            for _ in range(self.max_rounds):                                  # extend until the wavefront dies out
+                if len(frontier) == 0:
+                    break
+                cand = self.b.expand(frontier, np.full(len(frontier), w, np.float32), 6)
+                parent = np.repeat(np.arange(len(frontier)), 6)
+                keys = _pack(_cell_keys(cand["center"], self.origin, w))
+                free = np.array([k not in cells for k in keys.tolist()], bool)
+                # one candidate per free cell and round (first parent wins), like a cell being filled once
+                _, firsts = np.unique(keys, return_index=True)
+                uniq = np.zeros(len(keys), bool); uniq[firsts] = True
+                sel = free & uniq
+                if not sel.any():
+                    break
+                cand, parent = cand[sel], parent[sel]
+                res = self._optimize(cand)
+                good = res["status"] == 0
+                good &= (res["scale"] * 2.0 < w) & (res["scale"] * 2.0 > w / 2.0)
+                drift = np.linalg.norm(res["center"][:, :3] - frontier["center"][parent][:, :3], axis=1)
+                good &= drift < w * 1.5
+                t = time.perf_counter()
+                counts = self.b.accept(res, DEPTH_TEST_FACTOR)
+                self.stats.seconds_accept += time.perf_counter() - t
+                nimg = np.maximum(res["nimages"], 1)
+                good &= (counts[:, 0] >= MIN_IMAGES) & (counts[:, 1] < MIN_IMAGES)
+                good &= (counts[:, 2] >= MIN_IMAGES - 1) & (counts[:, 2] * 1.0 / nimg > 0.75)
+                acc = res[good]
+                if len(acc) == 0:
+                    break
+                live = self._insert(cells, acc, w)
+                new = acc[live]
+                self.b.depth_set(new)
+                n_ext += len(new)
+                frontier = new
+            patches = np.array(list(cells.values()), dtype=self.b.dtype) if cells else first[:0]
+            if level >= self.final_level or len(patches) == 0:
+                final.append(patches)
+                self.stats.per_level.append((level, n_ext, 0))
+                break
+            # branch into the next level: 4 candidates per patch, kept when they stay inside the parent's cell
+            cand = self.b.expand(patches, np.full(len(patches), w, np.float32), 4)
+            parent = np.repeat(np.arange(len(patches)), 4)
+            pkeys = _pack(_cell_keys(patches["center"], self.origin, w))[parent]
+            inside = _pack(_cell_keys(cand["center"], self.origin, w)) == pkeys
+            cand, parent, pkeys = cand[inside], parent[inside], pkeys[inside]
+            res = self._optimize(cand) if len(cand) else cand
+            keep = (res["status"] == 0) & (_pack(_cell_keys(res["center"], self.origin, w)) == pkeys) if len(cand) else np.zeros(0, bool)
+            children = res[keep]
+            branched_parents = np.unique(parent[keep]) if len(cand) else np.zeros(0, np.int64)
+            # cells that did not branch keep their patch as a final result (CellProcessor.cpp:266-269)
+            stay = np.ones(len(patches), bool); stay[branched_parents] = False
+            final.append(patches[stay])
+            self.stats.per_level.append((level, n_ext, int(len(children))))
+            cells = {}
+            level += 1
+            self._insert(cells, children, self.width(level))
+            self.b.depth_set(np.array(list(cells.values()), dtype=self.b.dtype) if cells else children[:0])
+        return np.concatenate(final) if final else seeds[:0]
