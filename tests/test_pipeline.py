@@ -12,8 +12,9 @@ from helpers import to_engine, to_oracle
 class OracleBackend:
     """CPU oracle behind the driver protocol (test infrastructure only)."""
 
-    def __init__(self, orc):
+    def __init__(self, orc, nthreads: int = 8):
         self.o = orc
+        self.nthreads = nthreads
         self.dtype = hp.PATCH_DTYPE
         self.o.depth_reset()
 
@@ -33,7 +34,7 @@ class OracleBackend:
         return out
 
     def optimize(self, rec):
-        res = self._from(self.o.optimize_batch(self._to(rec), nthreads=8))
+        res = self._from(self.o.optimize_batch(self._to(rec), nthreads=self.nthreads))
         bad = res["status"] != 0                      # the engine returns rejected patches as given, zeroed extras
         res["color"][bad] = 0; res["ncc"][bad] = 0
         res["images"][bad] = rec["images"][bad]
