@@ -255,7 +255,7 @@ void hpmvs_engine_destroy(hpmvs_engine_t* e) {
 }
 
 int hpmvs_engine_set_cameras(hpmvs_engine_t* e, int n, const hpmvs_camera_t* cams) {
-    if (!e || n <= 0 || !cams) return HPMVS_E_ARG;
+    if (!e || n <= 0 || n > 65535 || !cams) return HPMVS_E_ARG;      // view ids are carried as 16 bits on the device
     std::lock_guard<std::mutex> lk(e->mu);
     HP_CUDA(cudaSetDevice(e->device));
     if (n != e->ncams) {
@@ -463,6 +463,12 @@ int hpmvs_optimize_batch(hpmvs_engine_t* e, int n, const hpmvs_patch_t* in, hpmv
     if (rc) return rc;
     rc = ensure_patch_capacity(e, (size_t)n);
     if (rc) return rc;
+    // view ids index the camera table on the device: reject out-of-range ids here instead of faulting there
+    for (int i = 0; i < n; i++) {
+        const int k = in[i].nimages < HPMVS_MAX_VIEWS ? in[i].nimages : HPMVS_MAX_VIEWS;
+        for (int j = 0; j < k; j++)
+            if (in[i].images[j] < 0 || in[i].images[j] >= e->ncams) return HPMVS_E_ARG;
+    }
     HP_CUDA(cudaMemcpyAsync(e->d_in, in, sizeof(hpmvs_patch_t) * n, cudaMemcpyHostToDevice, s));
     rc = launch_optimize(e, n, e->d_in, e->d_out, s);
     if (rc) return rc;

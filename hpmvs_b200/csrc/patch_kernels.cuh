@@ -885,7 +885,8 @@ __device__ __noinline__ int serve_fill(LaneCtx& P, Scratch& W, const KParams& K,
         pi = __shfl_sync(FULL, pi, 0);
         if (pi >= K.n) return ST_DEAD;
         load_patch(P, K.in[pi], pi, lane);
-        const int st = pre_stage(W, P, K, lane);
+        // a view list longer than the engine's capacity is rejected, never truncated
+        const int st = (K.in[pi].nimages > MAXV) ? (int)HPMVS_FAIL_TOO_MANY_VIEWS : pre_stage(W, P, K, lane);
         if (st == HPMVS_OK) {
             __syncwarp();
             return ST_NEW;

@@ -132,6 +132,13 @@ def test_edge_cases(plane):
     assert got["status"][0] == 1 and got["status"][2] != 0
     ok = ref["status"] == 0
     assert np.array_equal(ref["center"][ok], got["center"][ok])
+    # engine limits are reported, not silently truncated / faulted
+    big = to_engine(seeds[:2]); big["nimages"][0] = hp.MAX_VIEWS + 1
+    r = eng.optimize(big)
+    assert r["status"][0] == 13 and r["nimages"][0] == hp.MAX_VIEWS + 1          # HPMVS_FAIL_TOO_MANY_VIEWS, record untouched
+    badid = to_engine(seeds[:2]); badid["images"][1, 0] = 999
+    with pytest.raises(hp.HpmvsError):
+        eng.optimize(badid)
 
 
 def test_size_independent_properties_large_batch():
