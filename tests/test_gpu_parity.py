@@ -183,3 +183,23 @@ def test_parked_variant_bit_exact(plane, monkeypatch):
         oracle.set_cr_asinf(False)
     st = compare_outputs(ref, b)
     assert st["status_equal"] == st["n"] and st["bit_exact"] == st["both_ok"] and st["vis_equal"] == st["both_ok"]
+
+
+def test_host_supplied_pyramid_levels(plane):
+    """The reference's callers hold the whole pyramid on the host (Image::load); uploading every level instead of
+    building levels 1..5 on the GPU must give the same results."""
+    sc, orc, seeds, eng = plane
+    eng2 = hp.Engine()
+    eng2.set_cameras(eng.cameras)
+    for cam in range(len(sc.cameras)):
+        for lvl in range(6):
+            eng2.upload_image(cam, lvl, orc.image(cam, lvl))
+    eng2.set_covis(orc.covis())
+    pe = to_engine(seeds[:120])
+    assert eng.optimize(pe).tobytes() == eng2.optimize(pe).tobytes()
+    # incomplete scenes are refused, not guessed
+    eng3 = hp.Engine()
+    eng3.set_cameras(eng.cameras)
+    eng3.upload_image(0, 0, sc.images[0])
+    with pytest.raises(hp.HpmvsError):
+        eng3.optimize(pe)
