@@ -12,7 +12,8 @@ One "step" = one pass of the hot path over one batch of seed patches (BASELINE.j
                  H2D of the batch + kernel + D2H of the results inside the timed region.
 * roofline     : algorithmic gather bytes (588 B per sampled 7x7x3 texture + 2*208 B record I/O per patch,
                  SURVEY section 8d) / kernel time, against the measured HBM peak in MEASURED_PEAKS.json.
-* cpu_baseline : the oracle (CPU restatement + the reference's real BOBYQA) on this box's host cores, bounded sample.
+* cpu_baseline : the reference's own PatchOptimizer (oracle/_ref/libhpmvs_ref.so, built from /root/reference's sources; falls back
+                 to the oracle restatement when that prebuilt library is absent) on this box's host cores, bounded sample.
 --impl reference times that CPU path alone with all host threads (the reference itself is CPU-only).
 """
 from __future__ import annotations
@@ -139,10 +140,23 @@ def host_threads() -> int:
         return os.cpu_count() or 1
 
 
-def cpu_reference_rate(scene, seeds_or, sample: int, threads: int, repeats: int = 1):
-    """Oracle on host cores: optimized patches/s on the first `sample` seeds (bounded CPU work)."""
+def cpu_arm(scene):
+    """The CPU implementation that is timed beside the engine: the reference's own PatchOptimizer (oracle/_ref/libhpmvs_ref.so,
+    compiled from /root/reference/src/hpmvs/*.cpp where they lie) when that prebuilt library is present -> kind "reference";
+    otherwise the oracle restatement linked to the reference's BOBYQA -> kind "port".  Returns (scene object, kind, description)."""
     import oracle
-    orc = oracle.OracleScene.from_synth(scene)
+    from oracle import ref
+    if ref.available() and not os.environ.get("HPMVS_BENCH_FORCE_PORT"):
+        return ref.RefScene.from_synth(scene), "reference", \
+            "the reference's own mo3d::PatchOptimizer::optimize (its sources compiled with -O3 + OpenMP as CMakeLists.txt:4-7; " \
+            "Eigen/glog stood in for by oracle/shim), one optimizer per thread as src/main.cpp:123-125, OpenMP over patches as Scene.cpp:114"
+    return oracle.OracleScene.from_synth(scene), "port", \
+        "oracle restatement of PatchOptimizer + the reference's real nlopt BOBYQA, OpenMP over patches as Scene.cpp:114"
+
+
+def cpu_reference_rate(scene, seeds_or, sample: int, threads: int, repeats: int = 1):
+    """CPU arm on host cores: optimized patches/s on the first `sample` seeds (bounded CPU work)."""
+    orc, kind, how = cpu_arm(scene)
     batch = seeds_or[:sample]
     best = None
     ok = 0
@@ -152,7 +166,7 @@ def cpu_reference_rate(scene, seeds_or, sample: int, threads: int, repeats: int 
         dt = time.perf_counter() - t0
         ok = int((out["status"] == 0).sum())
         best = dt if best is None else min(best, dt)
-    return ok / best, best, ok, len(batch)
+    return ok / best, best, ok, len(batch), kind, how
 
 
 def to_oracle(p_en):
@@ -165,15 +179,15 @@ def to_oracle(p_en):
 
 
 def run_reference(args):
-    """--impl reference: the CPU path (oracle port + the reference's real BOBYQA) with all host threads."""
+    """--impl reference: the reference's CPU implementation of the path with all host threads (see cpu_arm)."""
     import oracle
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     scene, desc = cached_scene(args.workload, 0)
-    orc = oracle.OracleScene.from_synth(scene)
-    seeds, valid = orc.seed_patches(scene.points, scene.meas_offsets, scene.meas_cam)
+    seeds, valid = oracle.OracleScene.from_synth(scene).seed_patches(scene.points, scene.meas_offsets, scene.meas_cam)
     seeds = seeds[valid]
+    orc, kind, how = cpu_arm(scene)
     threads = host_threads()
     # each step = a bounded sample of the workload: ~2 s of wall time per step at ~1.7k patches/s/thread
     sample = args.cpu_sample or int(min(len(seeds), max(256, 3000 * threads // 8)))
@@ -191,9 +205,8 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 samples / f64 optimizer", "data": "synthetic",
             "config": {"workload": desc, "patches_per_step": int(sample)},
-            "cpu_baseline": {"value": val, "unit": "patches/s", "cores": threads, "kind": "port",
-                             "sample": f"first {sample} of {len(seeds)} seed patches per step, oracle restatement of PatchOptimizer "
-                                       f"+ the reference's real nlopt BOBYQA, OpenMP over patches as Scene.cpp:114"},
+            "cpu_baseline": {"value": val, "unit": "patches/s", "cores": threads, "kind": kind,
+                             "sample": f"first {sample} of {len(seeds)} seed patches per step; {how}"},
             "e2e": {"value": val, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -343,10 +356,9 @@ def main():
             import oracle
             threads = host_threads()
             sample = args.cpu_sample or int(min(n, max(512, 4000 * threads // 8)))
-            rate, dt, okc, ns = cpu_reference_rate(scene, to_oracle(seeds), sample, threads)
-            cpu = {"value": rate, "unit": "patches/s", "cores": threads, "kind": "port",
-                   "sample": f"first {ns} of {n} seed patches of the same batch, {okc} optimized, {dt:.2f} s wall; oracle restatement of "
-                             f"PatchOptimizer + the reference's real nlopt BOBYQA (HPMVS itself cannot be built here), OpenMP over patches"}
+            rate, dt, okc, ns, kind, how = cpu_reference_rate(scene, to_oracle(seeds), sample, threads)
+            cpu = {"value": rate, "unit": "patches/s", "cores": threads, "kind": kind,
+                   "sample": f"first {ns} of {n} seed patches of the same batch, {okc} optimized, {dt:.2f} s wall; {how}"}
         line = {"metric": "optimized patches/sec", "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": 1e3 * t_dev_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 samples / f64 optimizer", "data": "synthetic",

@@ -72,7 +72,8 @@ int hpmvs_camera_from_nvm(double f, const double q[4], const double c[3], int wi
         }
     out->center[0] = cf[0]; out->center[1] = cf[1]; out->center[2] = cf[2]; out->center[3] = 1.0f;
     const Vec3 row2{out->P[0][2][0], out->P[0][2][1], out->P[0][2][2]};
-    const float n2 = sqrtf(dot(row2, row2));
+    // row(2).head(3).norm(): a dynamic-size block, reduced by Eigen's scalar loop (a0+a1)+a2 (Camera.cpp:71)
+    const float n2 = sqrtf((row2.x * row2.x + row2.y * row2.y) + row2.z * row2.z);
     const Vec3 zax{row2.x / n2, row2.y / n2, row2.z / n2};
     const Vec3 row0{out->P[0][0][0], out->P[0][0][1], out->P[0][0][2]};
     const Vec3 yax = unit(cross(zax, row0));

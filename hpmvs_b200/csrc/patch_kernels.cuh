@@ -203,7 +203,12 @@ __device__ __forceinline__ f3 get_color(const uchar4* img, int pitch, float x, f
 // calculatePatchAxis (:532-548): all lanes compute the same registers
 // ----------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void patch_axes(const DevCamera& rc, f4 n, float scale, f4& xa, f4& ya, f4& za) {
-    f3 z = normalized3(f3{n.x, n.y, n.z});
+    // n.head(3).normalized() (PatchOptimizer.cpp:536): dynamic-size block -> Eigen's scalar reduction loop (a0+a1)+a2
+    f3 z = f3{n.x, n.y, n.z};
+    {
+        const float zz = (n.x * n.x + n.y * n.y) + n.z * n.z;
+        if (zz > 0.0f) { const float s = sqrtf(zz); z = f3{n.x / s, n.y / s, n.z / s}; }
+    }
     f3 y = normalized3(cross3(z, f3{rc.xaxis[0], rc.xaxis[1], rc.xaxis[2]}));
     f3 x = normalized3(cross3(y, z));
     x.x *= scale; x.y *= scale; x.z *= scale;

@@ -6,7 +6,9 @@
 //   * Eigen >= 3.3 semantics, x86-64 baseline (SSE2 on, no FMA, no AVX: CMakeLists.txt:4-7 sets
 //     only -std=c++11 -O3):
 //       - Vector4f reductions (dot/squaredNorm) are SSE2-vectorised: (a0+a2)+(a1+a3)
-//       - Vector3f / Block<.,3,1> / Vector2f reductions are unrolled binary trees: a0+(a1+a2)
+//       - Vector3f / Vector2f (fixed size, no packet access) reductions are unrolled binary trees: a0+(a1+a2)
+//       - DYNAMIC-size blocks (n.head(3), row(2).head(3): Block<.,Dynamic,1>) are not unrolled and are below one
+//         packet: Redux.h takes its scalar loop (a0+a1)+a2 - used at PatchOptimizer.cpp:536 and Camera.cpp:71
 //       - fixed-size matrix*vector is coefficient based: inner 4 -> (p0+p1)+(p2+p3), inner 3 -> p0+(p1+p2)
 //       - normalized(): z=squaredNorm; if (z>0) v / sqrt(z)  (true division per element)
 //       - double scalars multiplying float vectors are narrowed to float first
@@ -70,6 +72,13 @@ inline V3 cross3(const V3& a, const V3& b) {
     return V3{{a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]}};
 }
 inline V3 head3(const V4& a) { return V3{{a[0], a[1], a[2]}}; }
+// reductions over a dynamic-size head(3) block: scalar loop, (a0+a1)+a2
+inline float sqnorm3_dyn(const V3& a) { return (a[0] * a[0] + a[1] * a[1]) + a[2] * a[2]; }
+inline V3 normalized3_dyn(const V3& a) {
+    const float z = sqnorm3_dyn(a);
+    if (z > 0.0f) { const float s = std::sqrt(z); return V3{{a[0] / s, a[1] / s, a[2] / s}}; }
+    return a;
+}
 
 // ------------------------------------------------------------------------------------------
 // Scene data
@@ -140,7 +149,7 @@ void camera_init(Camera& cam, double f, const double q[4], const double c[3], in
     cam.center = V4{{cf[0], cf[1], cf[2], 1.0f}};
     // oAxis_ = row(2) / row(2).head(3).norm()   (Camera.cpp:66-67)
     const V3 r2{{cam.P[0][2][0], cam.P[0][2][1], cam.P[0][2][2]}};
-    const float n2 = norm3(r2);
+    const float n2 = std::sqrt(sqnorm3_dyn(r2));   // row(2).head(3).norm(): dynamic size
     cam.zAxis = V3{{r2[0] / n2, r2[1] / n2, r2[2] / n2}};
     const V3 r0{{cam.P[0][0][0], cam.P[0][0][1], cam.P[0][0][2]}};
     cam.yAxis = normalized3(cross3(cam.zAxis, r0));
@@ -282,7 +291,7 @@ struct PatchOptimizer {
     // :532-548
     void calculatePatchAxis(int refIndex, const V4& n, float scale) {
         const Camera& rc = scene->cameras[refIndex];
-        V3 z = normalized3(head3(n));
+        V3 z = normalized3_dyn(head3(n));   // n.head(3).normalized(): dynamic size
         V3 y = normalized3(cross3(z, rc.xAxis));
         V3 x = normalized3(cross3(y, z));
         for (int i = 0; i < 3; i++) { x[i] *= scale; y[i] *= scale; }

@@ -13,11 +13,16 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.  The product (hpmvs_b200/) never does.
  *
- * PARITY STATUS: the HPMVS reference ships no golden vectors and cannot be built here (Eigen3,
- * libjpeg, gflags, glog absent) => the PatchOptimizer restatement is "parity unpinned" against
- * HPMVS itself.  The optimizer component IS pinned: it is the reference's own BOBYQA object code,
- * and tests/test_oracle.py checks it against nlopt's known-answer functions
- * (thirdLibs/nlopt-2.4.2/test/testfuncs.c:65-89,445-447).
+ * PARITY STATUS: pinned against the reference's own code.  HPMVS ships no golden vectors, but its sources compile
+ * here where they lie (oracle/Makefile `refhpmvs` -> oracle/_ref/libhpmvs_ref.so + the hpmvs_ref CLI) once its
+ * external dependencies that this image lacks are stood in for (oracle/shim: Eigen with its published evaluation
+ * order restated, glog, gflags, jpeglib declarations).  tests/test_reference_golden.py checks this restatement
+ * bit for bit against that build - Camera::init, the CImg pyramid, covisibility, seeds, optimize() (centre, normal,
+ * views, colour, success), Scene::initPatches run whole, setDepths and the three acceptance tests - live and through
+ * committed fixtures (tests/golden/ref_*.npz).  What stays unpinned is Eigen itself (absent, not vendored, no version
+ * pinned by the reference): the shim's evaluation-order rules are documented in oracle/shim/Eigen/Dense.
+ * The optimizer component is the reference's own BOBYQA object code; tests/test_oracle.py also checks it against
+ * nlopt's known-answer functions (thirdLibs/nlopt-2.4.2/test/testfuncs.c:65-89,445-447).
  */
 #ifndef HPMVS_ORACLE_H
 #define HPMVS_ORACLE_H
