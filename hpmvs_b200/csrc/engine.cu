@@ -621,7 +621,7 @@ int hpmvs_engine_counters(hpmvs_engine_t* e, hpmvs_counters_t* out, int reset) {
         const char* names[13] = {"AFTER_EVAL", "RESCUE_LOOP", "RESCUE_DONE", "GOPT_FIX", "FARPOINT", "REDUCE_RHO", "TRUST", "SHIFT", "RESCUE", "ALTMOV", "VLAG", "EVAL", "EXIT"};
         for (int i = 0; i < 13; i++)
             if (pt[i]) fprintf(stderr, "[hpmvs profile]   %-12s trips %10llu  cycles/trip %8.0f  lanes/trip %5.1f  total Gcyc %7.2f\n", names[i], pt[i], (double)pc[i] / pt[i], (double)pl[i] / pt[i], pc[i] / 1e9);
-        fprintf(stderr, "[hpmvs profile] opt: wait %llu adv %llu rounds %llu lanes %llu | sampler: idle %llu eval %llu n_eval %llu\n", c[4], c[5], c[6], c[7], c[8], c[9], c[10]);
+        fprintf(stderr, "[hpmvs profile] opt: wait %llu adv %llu rounds %llu lanes %llu | sampler: idle %llu eval %llu n_eval %llu | parked: copy %llu sampler_other %llu\n", c[4], c[5], c[6], c[7], c[8], c[9], c[10], c[11], c[12]);
 #endif
     }
     out->patches = c[0]; out->patches_ok = c[1]; out->evals = c[2]; out->textures = c[3];

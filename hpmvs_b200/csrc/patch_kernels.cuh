@@ -1024,9 +1024,11 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
                 __syncwarp();
                 const int ns = serve_fill(P, W, K, lane, cnt);
                 if (lane == 0) st_state(&C.sstate[slot], ns);
+                t_other += HP_CLOCK() - tq1;
             } else {   // REQ_FILL
                 const int ns = serve_fill(P, W, K, lane, cnt);
                 if (lane == 0) st_state(&C.sstate[slot], ns);
+                t_other += HP_CLOCK() - tq1;
             }
             __syncwarp();
         }
@@ -1037,7 +1039,7 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
 #ifdef HP_PROFILE
         if (lane == 0) {
             atomicAdd(&K.counters[8], (unsigned long long)t_idle); atomicAdd(&K.counters[9], (unsigned long long)t_eval);
-            atomicAdd(&K.counters[10], (unsigned long long)n_eval);
+            atomicAdd(&K.counters[10], (unsigned long long)n_eval); atomicAdd(&K.counters[12], (unsigned long long)t_other);
         }
 #endif
         (void)t_other;
@@ -1112,6 +1114,8 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
         LaneCtx& mine = C.stage_ctx[warp * LPW + (lane < LPW ? lane : 0)];
         bq3::State& bq = C.stage_bq[warp * LPW + (lane < LPW ? lane : 0)].s;
         int tries = 0;
+        long long t_wait = 0, t_adv = 0, t_copy = 0, n_rounds = 0, n_lanes = 0;
+        long long tw0 = HP_CLOCK();
         for (;;) {
             // ---- claim up to LPW ready slots of this warp's range ---------------------------------------------
             int count = 0, npend = 0, nlive = 0;
@@ -1135,6 +1139,8 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
             if (count < MIN_BATCH && npend > 0 && tries < 40) { ++tries; __nanosleep(500); continue; }
             tries = 0;
             __threadfence_block();
+            const long long tc0 = HP_CLOCK();
+            t_wait += tc0 - tw0; n_rounds++; n_lanes += count;
             // ---- stage in: context always, optimizer state unless the patch is new -------------------------------
             for (int j = 0; j < count; j++) {
                 const int e = C.claim[warp][j], slot = e & 0xffff;
@@ -1142,6 +1148,8 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
                 if (!(e >> 16)) copy_in<BQ_COPY_BYTES>(&C.stage_bq[warp * LPW + j], &pool_bq[slot], lane);
             }
             __syncwarp();
+            const long long ta0 = HP_CLOCK();
+            t_copy += ta0 - tc0;
             // ---- advance lane-parallel ------------------------------------------------------------------------------
             int st = 0, slot = 0;
             if (lane < count) {
@@ -1176,6 +1184,8 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
                 }
             }
             __syncwarp();
+            const long long to0 = HP_CLOCK();
+            t_adv += to0 - ta0;
             // ---- stage out and publish ------------------------------------------------------------------------------
             for (int j = 0; j < count; j++) {
                 const int sl = C.claim[warp][j] & 0xffff;
@@ -1189,7 +1199,16 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
                 q_push(C.Q, st == ST_EVAL_PENDING ? REQ_EVAL : REQ_POST, slot);
             }
             __syncwarp();
+            tw0 = HP_CLOCK();
+            t_copy += tw0 - to0;
         }
+#ifdef HP_PROFILE
+        if (lane == 0) {
+            atomicAdd(&K.counters[4], (unsigned long long)t_wait); atomicAdd(&K.counters[5], (unsigned long long)t_adv);
+            atomicAdd(&K.counters[6], (unsigned long long)n_rounds); atomicAdd(&K.counters[7], (unsigned long long)n_lanes);
+            atomicAdd(&K.counters[11], (unsigned long long)t_copy);
+        }
+#endif
         __syncwarp();
         if (lane == 0) {
             if (atomicSub(&C.Q.opt_alive, 1) == 1)
@@ -1200,8 +1219,12 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
         Scratch& W = C.samp[warp - OPT_WARPS].S;
         LaneCtx& P = C.samp[warp - OPT_WARPS].P;
         unsigned long long cnt[4] = {0, 0, 0, 0};
+        long long t_idle = 0, t_eval = 0, t_other = 0, n_eval = 0;
         for (;;) {
+            const long long tq0 = HP_CLOCK();
             const int e = q_pop(C.Q, lane);
+            const long long tq1 = HP_CLOCK();
+            t_idle += tq1 - tq0;
             const int kind = e >> 16, slot = e & 0xffff;
             if (kind == REQ_EXIT) break;
             int ns = -1;
@@ -1218,6 +1241,7 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
                     *reinterpret_cast<volatile double*>(&C.fval[slot]) = f;
                     st_state(&C.sstate[slot], ST_EVAL_DONE);
                 }
+                t_eval += HP_CLOCK() - tq1; n_eval++;
             } else {
                 if (kind == REQ_POST) {
                     copy_in<(int)sizeof(LaneCtx)>(&P, &pool_ctx[slot], lane);
@@ -1234,6 +1258,7 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
                 __threadfence();
                 __syncwarp();
                 if (lane == 0) st_state(&C.sstate[slot], ns);
+                t_other += HP_CLOCK() - tq1;
             }
             __syncwarp();
         }
@@ -1241,6 +1266,13 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
             atomicAdd(&K.counters[0], cnt[0]); atomicAdd(&K.counters[1], cnt[1]);
             atomicAdd(&K.counters[2], cnt[2]); atomicAdd(&K.counters[3], cnt[3]);
         }
+#ifdef HP_PROFILE
+        if (lane == 0) {
+            atomicAdd(&K.counters[8], (unsigned long long)t_idle); atomicAdd(&K.counters[9], (unsigned long long)t_eval);
+            atomicAdd(&K.counters[10], (unsigned long long)n_eval); atomicAdd(&K.counters[12], (unsigned long long)t_other);
+        }
+#endif
+        (void)t_other; (void)t_eval; (void)n_eval; (void)t_idle;
     }
 }
 

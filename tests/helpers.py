@@ -54,4 +54,5 @@ def compare_outputs(ref: np.ndarray, got: np.ndarray):
         st["max_dcenter_over_scale"] = float(dc.max())
         st["max_dnormal"] = float(dn.max())
         st["max_dscore"] = float(np.abs(ref["last_val"][ok] - got["score"][ok]).max())
+        st["dcenter_over_scale"], st["dnormal"], st["dscore"] = dc, dn, np.abs(ref["last_val"][ok] - got["score"][ok])
     return st

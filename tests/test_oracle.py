@@ -116,3 +116,21 @@ def test_golden_fixture():
         oracle.set_cr_asinf(False)
     for f in ("status", "center", "normal", "nimages", "images", "color", "evals"):
         assert np.array_equal(out[f], g[f]), f
+
+
+def test_asinf_mode_spread():
+    # The reference calls std::asin(float) (PatchOptimizer.cpp:427); this image's glibc 2.39 asinf is not correctly rounded
+    # for a few percent of inputs.  One ulp in the starting angle leaves >= 90 % of the patches bit-identical, nearly all
+    # others within a few 1e-3 of the patch scale, and lets the rare patch slide along a flat valley of the objective.
+    sc, orc, seeds = small_plane()
+    oracle.set_cr_asinf(True)
+    try:
+        a = orc.optimize_batch(seeds, nthreads=4)
+    finally:
+        oracle.set_cr_asinf(False)
+    b = orc.optimize_batch(seeds, nthreads=4)
+    assert np.array_equal(a["status"], b["status"])
+    ok = a["status"] == 0
+    assert np.array_equal(a["nimages"][ok], b["nimages"][ok]) and np.array_equal(a["images"][ok], b["images"][ok])
+    dc = np.linalg.norm(a["center"][ok][:, :3] - b["center"][ok][:, :3], axis=1) / a["scale"][ok]
+    assert (dc == 0).mean() >= 0.9 and (dc < 0.05).mean() >= 0.99 and dc.max() < 0.5
