@@ -308,6 +308,31 @@ def main():
     out_np = h_out.numpy().view(hp.PATCH_DTYPE).reshape(n)
     ok_e2e = int((out_np["status"] == 0).sum())
 
+    # ---- the stand-alone scoring kernel (K1 = PatchOptimizer::setINCCs for a batch: the gather + NCC part of the path without the
+    # optimizer around it), device-resident records, timed with CUDA events; reported as `roofline_ncc` ------------------------------
+    reps = max(1, 200000 // max(n, 1))
+    d_big = d_in.repeat(reps, 1).contiguous()
+    nb = n * reps
+    d_inc = torch.empty((nb, hp.MAX_VIEWS), dtype=torch.float32, device="cuda")
+    for _ in range(2):
+        eng.ncc_device(nb, d_big.data_ptr(), d_inc.data_ptr(), 0, False, sptr)
+    torch.cuda.synchronize()
+    eng.counters(reset=True)
+    ncc_evs = []
+    for _ in range(max(3, args.steps // 2)):
+        flush.zero_()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        eng.ncc_device(nb, d_big.data_ptr(), d_inc.data_ptr(), 0, False, sptr)
+        e1.record(stream)
+        ncc_evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ncc_ms = [a.elapsed_time(b) for a, b in ncc_evs]
+    ncc_cnt = eng.counters(reset=True)
+    ncc_tex_per_launch = ncc_cnt.textures / len(ncc_ms)
+    ncc_launch_s = sum(ncc_ms) / len(ncc_ms) / 1e3
+    del d_big, d_inc
+
     # ---- final exchange (untimed for `value`): variable-length NCCL gather of the patch records + border de-dup ----
     gather_ms, merged = None, None
     if dist is not None:
@@ -375,6 +400,13 @@ def main():
                              "traffic": traffic, "peak_source": peak_src, "kernel": "hp::optimize_kernel",
                              "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": 1e3 * mean_launch_s,
                              "note": "algorithmic gather bytes (588 B/texture, no reuse credit); the footprint is L1-resident so DRAM traffic is far lower - kernel is issue/latency bound, see DESIGN.md"},
+                "roofline_ncc": {"bound": "hbm", "kernel": "hp::ncc_kernel (setINCCs for a batch: projection, 7x7 bilinear RGB gather, normalise, NCC)",
+                                 "achieved": (TEX_BYTES * ncc_tex_per_launch + (REC_BYTES + 4 * hp.MAX_VIEWS) * nb) / ncc_launch_s / 1e9,
+                                 "peak": peak, "unit": "GB/s",
+                                 "frac": (TEX_BYTES * ncc_tex_per_launch + (REC_BYTES + 4 * hp.MAX_VIEWS) * nb) / ncc_launch_s / 1e9 / peak,
+                                 "patches_per_launch": int(nb), "textures_per_launch": ncc_tex_per_launch, "launch_ms": 1e3 * ncc_launch_s,
+                                 "patch_scores_per_s": nb / ncc_launch_s, "traffic": None,
+                                 "note": "secondary figure: the scoring part of the path alone; issue-bound (see profiles/), not counted in value/e2e"},
                 "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if dist is not None:

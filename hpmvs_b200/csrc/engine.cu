@@ -206,7 +206,7 @@ int hpmvs_engine_create(const hpmvs_options_t* opt, int device, hpmvs_engine_t**
     HP_CUDA(cudaMalloc(&e->d_work, sizeof(int)));
     HP_CUDA(cudaMalloc(&e->d_counters, 16 * sizeof(unsigned long long)));
     HP_CUDA(cudaMemset(e->d_counters, 0, 16 * sizeof(unsigned long long)));
-    e->smem_bytes = sizeof(hp::WarpShared) * hp::WARPS_PER_BLOCK;          // ncc_kernel
+    e->smem_bytes = sizeof(hp::NccWarp) * hp::WARPS_PER_BLOCK;             // ncc_kernel
     e->variant = g_default_variant;
     if (const char* cfg = getenv("HPMVS_CONFIG")) {
         int ow = 0, sw = 0, lpw = 0;
@@ -507,6 +507,28 @@ int hpmvs_ncc_batch(hpmvs_engine_t* e, int n, const hpmvs_patch_t* in, int ref_i
     HP_CUDA(cudaGetLastError());
     HP_CUDA(cudaMemcpyAsync(inccs, e->d_inccs, ni * sizeof(float), cudaMemcpyDeviceToHost, s));
     HP_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int hpmvs_ncc_batch_device(hpmvs_engine_t* e, int n, const hpmvs_patch_t* d_in, int ref_idx, int robust, float* d_inccs, void* stream) {
+    if (!e || n < 0 || ref_idx < 0 || ref_idx >= HPMVS_MAX_VIEWS || (n > 0 && (!d_in || !d_inccs))) return HPMVS_E_ARG;
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(e->mu);
+    HP_CUDA(cudaSetDevice(e->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    int rc = check_ready(e);
+    if (rc) return rc;
+    rc = sync_cameras(e);
+    if (rc) return rc;
+    const hp::KParams K = make_params(e, d_in, e->d_out, n);
+    int grid = e->sm_count * e->blocks_per_sm;
+    const int need = (n + hp::WARPS_PER_BLOCK - 1) / hp::WARPS_PER_BLOCK;
+    if (need < grid) grid = need;
+    HP_CUDA(cudaEventRecord(e->ev0, s));
+    hp::ncc_kernel<<<grid, hp::WARPS_PER_BLOCK * 32, e->smem_bytes, s>>>(K, ref_idx, robust, d_inccs);
+    HP_CUDA(cudaEventRecord(e->ev1, s));
+    e->launches++;
+    HP_CUDA(cudaGetLastError());
     return 0;
 }
 

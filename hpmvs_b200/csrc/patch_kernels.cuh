@@ -130,6 +130,11 @@ struct __align__(16) WarpShared {
     Scratch S;
     LaneCtx ctx[32];
 };
+// one warp of the stand-alone scoring kernel (K1): 7 KB, so that 28 warps are resident per SM
+struct __align__(16) NccWarp {
+    Scratch S;
+    LaneCtx P;
+};
 
 // ----------------------------------------------------------------------------------------------------------
 // f32 helpers in Eigen's evaluation order (see oracle/hpmvs_oracle.cpp header for the conventions)
@@ -1281,9 +1286,9 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
 // ----------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) ncc_kernel(const KParams K, int ref_idx, int robust, float* inccs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    WarpShared& WS = reinterpret_cast<WarpShared*>(smem_raw)[threadIdx.x >> 5];
+    NccWarp& WS = reinterpret_cast<NccWarp*>(smem_raw)[threadIdx.x >> 5];
     Scratch& W = WS.S;
-    LaneCtx& P = WS.ctx[0];
+    LaneCtx& P = WS.P;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;

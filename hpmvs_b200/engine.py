@@ -70,6 +70,7 @@ def _lib():
         L.hpmvs_optimize_batch.argtypes = [vp, C.c_int, vp, vp, vp]
         L.hpmvs_optimize_batch_device.argtypes = [vp, C.c_int, vp, vp, vp]
         L.hpmvs_ncc_batch.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, fp, vp]
+        L.hpmvs_ncc_batch_device.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, vp]
         L.hpmvs_engine_counters.argtypes = [vp, C.POINTER(Counters), C.c_int]
         L.hpmvs_engine_stream.argtypes = [vp]; L.hpmvs_engine_stream.restype = vp
         L.hpmvs_engine_last_kernel_ms.argtypes = [vp]; L.hpmvs_engine_last_kernel_ms.restype = C.c_float
@@ -227,6 +228,10 @@ class Engine:
         out = np.zeros((len(patches), MAX_VIEWS), np.float32)
         _check(_lib().hpmvs_ncc_batch(self._h, len(patches), patches.ctypes.data, ref_idx, 1 if robust else 0, _p(out, C.c_float), None))
         return out
+
+    def ncc_device(self, n: int, d_in: int, d_inccs: int, ref_idx: int = 0, robust: bool = False, stream: int = 0) -> None:
+        """Same scoring on device-resident records / results ([n, MAX_VIEWS] f32), asynchronous on `stream`."""
+        _check(_lib().hpmvs_ncc_batch_device(self._h, n, d_in, ref_idx, 1 if robust else 0, d_inccs, stream or None))
 
     # -- "next" rows: depth maps + acceptance tests --------------------------------------------
     def depth_reset(self) -> None:

@@ -140,6 +140,10 @@ int  hpmvs_optimize_batch_device(hpmvs_engine_t *e, int n, const hpmvs_patch_t *
  * inccs[i*HPMVS_MAX_VIEWS + k] = (robust ? r/(1+3r) : r), r = 1-NCC(view ref_idx, view k); 2.0 where invalid. */
 int  hpmvs_ncc_batch(hpmvs_engine_t *e, int n, const hpmvs_patch_t *in, int ref_idx, int robust, float *inccs,
                      void *stream);
+/* Same scoring on device-resident records and a device-resident result array (n * HPMVS_MAX_VIEWS floats): no copies,
+ * asynchronous on `stream`; hpmvs_engine_last_kernel_ms() then reports this kernel's duration. */
+int  hpmvs_ncc_batch_device(hpmvs_engine_t *e, int n, const hpmvs_patch_t *d_in, int ref_idx, int robust,
+                            float *d_inccs, void *stream);
 
 /* ---- "next" rows: what CellProcessor::extend / branch do right around optimize() ---------------------------------- */
 
@@ -208,7 +212,8 @@ int  hpmvs_ply_write_ext(const char *path, int n, const hpmvs_patch_t *patches, 
 int  hpmvs_engine_counters(hpmvs_engine_t *e, hpmvs_counters_t *out, int reset);
 /* The engine's own stream as a cudaStream_t, so callers can record events around asynchronous calls. */
 void *hpmvs_engine_stream(hpmvs_engine_t *e);
-/* Device-side duration of the most recent fused optimize kernel in milliseconds (CUDA events on its stream). */
+/* Device-side duration of the most recent fused optimize kernel (or *_device scoring kernel) in milliseconds (CUDA events
+ * on its stream). */
 float hpmvs_engine_last_kernel_ms(hpmvs_engine_t *e);
 const char *hpmvs_error_string(int code);
 int  hpmvs_abi_version(void);

@@ -59,6 +59,18 @@ def test_setinccs_bit_exact(plane):
             assert np.array_equal(ref, got[i, :len(ref)]), (ref_idx, robust, i)
 
 
+def test_setinccs_device_resident_call(plane):
+    import torch
+    sc, orc, seeds, eng = plane
+    pe = to_engine(seeds)
+    d_in = torch.from_numpy(pe.view(np.uint8).reshape(len(pe), -1).copy()).cuda()
+    d_out = torch.full((len(pe), hp.MAX_VIEWS), -1.0, dtype=torch.float32, device="cuda")
+    eng.ncc_device(len(pe), d_in.data_ptr(), d_out.data_ptr(), 1, True)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), eng.ncc(pe, 1, True))
+    assert eng.last_kernel_ms() > 0.0
+
+
 def test_optimize_bit_exact_with_correctly_rounded_asinf(plane):
     sc, orc, seeds, eng = plane
     oracle.set_cr_asinf(True)
