@@ -19,7 +19,8 @@ HEADERS = [os.path.join(_HERE, "csrc", "patch_kernels.cuh"), os.path.join(_HERE,
 
 # -fmad=false / -ffp-contract=off: the kernels restate the reference's f32/f64 evaluation order (see
 # patch_kernels.cuh); FMA contraction would change roundings and break the reproducible BOBYQA trajectory.
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+# -DBQ_DEFER_TRUST=1: a second trust-region step inside one optimizer round is deferred to the next round (bobyqa3.h)
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false", "-DBQ_DEFER_TRUST=1",
               "-Xcompiler", "-fPIC,-ffp-contract=off", "-diag-suppress", "550,177", "-shared"]
 
 
@@ -36,6 +37,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     extra = ["-DHP_PROFILE"] if os.environ.get("HPMVS_BUILD_PROFILE") else []
+    extra += os.environ.get("HPMVS_BUILD_DEFS", "").split()          # e.g. "-DBQ_DEFER_TRUST=8" for A/B builds (with HPMVS_LIB)
     cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

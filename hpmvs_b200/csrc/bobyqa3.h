@@ -88,7 +88,19 @@ enum Result : int {
     R_SUCCESS = 1, R_XTOL_REACHED = 4, R_MAXEVAL_REACHED = 5
 };
 
-enum Action : int { ASK = 0, DONE = 1 };
+enum Action : int { ASK = 0, DONE = 1, YIELD = 2 };   // YIELD (device, optional): call advance() again, no objective value needed
+
+// BQ_DEFER_TRUST=<lanes>: a lane that needs a SECOND trust-region step inside one advance() call (after a rho reduction)
+// gives the step back to the caller instead of making the whole warp wait for a trsbox trip with one or two lanes in it;
+// it joins the first trip of the next round.  Only when at least <lanes> lanes entered together (busy rounds).
+#ifndef BQ_DEFER_TRUST
+#define BQ_DEFER_TRUST 0
+#endif
+#ifndef BQ_ALTSEARCH_UNROLL
+#define BQ_ALTSEARCH_UNROLL 1
+#endif
+#define BQ_PRAGMA_(x) _Pragma(#x)
+#define BQ_PRAGMA_UNROLL_N(n) BQ_PRAGMA_(unroll n)
 
 BQ_HD double dmin(double a, double b) { return a <= b ? a : b; }
 BQ_HD double dmax(double a, double b) { return a >= b ? a : b; }
@@ -114,7 +126,7 @@ struct State {
 
 // program counters (resume points)
 enum : int {
-    PC_PRELIM_EVAL = 1, PC_MAIN_EVAL = 2, PC_RESCUE_EVAL = 3, PC_FINISHED = 4
+    PC_PRELIM_EVAL = 1, PC_MAIN_EVAL = 2, PC_RESCUE_EVAL = 3, PC_FINISHED = 4, PC_YIELD_TRUST = 5
 };
 
 // labels of the main iteration, numbered in flow order (the warp scheduler runs the smallest one present)
@@ -552,7 +564,10 @@ BQ_HDN void trsbox(State& S, unsigned wmask) {
             double redmax = 0.0, redsav = 0.0, rdprev = 0.0, rdnext = 0.0;
             int isav = 0;
             const int iu = (int)(angbd * 17. + 3.1);
-            BQ_NOUNROLL for (int i = 1; i <= iu; i++) {
+#if defined(__CUDA_ARCH__)
+            BQ_PRAGMA_UNROLL_N(BQ_ALTSEARCH_UNROLL)
+#endif
+            for (int i = 1; i <= iu; i++) {
                 const double angt = angbd * (double)i / (double)iu;
                 const double sth = (angt + angt) / (1.0 + angt * angt);
                 const double temp = shs + angt * (angt * dhd - dhs - dhs);
@@ -1036,6 +1051,9 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
             lbl = L_GOPT_FIX;
         }
         }
+    } else if (S.pc == PC_YIELD_TRUST) {
+        S.pc = PC_MAIN_EVAL;
+        lbl = L_TRUST;
     } else if (S.pc == PC_MAIN_EVAL) {
         S.nevals++;
         S.f = f_in;
@@ -1057,6 +1075,8 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
         }
     }
 
+    int ntrust = 0;   // trust-region steps taken in this call (BQ_DEFER_TRUST)
+    (void)ntrust;
     for (;;) {
         BQ_SCHED_BEGIN(wmask, done, lbl)
 #if defined(__CUDA_ARCH__)
@@ -1093,6 +1113,14 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
         }
         // -------------------------------------------------------------- trust-region step
         case L_TRUST: {
+#if defined(__CUDA_ARCH__) && BQ_DEFER_TRUST > 0
+            if (ntrust >= 1 && __popc(wmask) >= BQ_DEFER_TRUST) {
+                S.pc = PC_YIELD_TRUST;
+                result = YIELD; done = true;
+                break;
+            }
+            ++ntrust;
+#endif
             trsbox(S, sel);
             S.dnorm = dmin(S.delta, sqrt(S.dsq));
             if (S.dnorm < 0.5 * S.rho) {

@@ -71,6 +71,11 @@ struct hpmvs_engine {
     hpmvs_patch_t* d_out = nullptr;
     float* d_inccs = nullptr;
     size_t cap_patches = 0, cap_inccs = 0;
+    int start_mode = 0;              // hpmvs_engine_set_start_mode
+    double* d_start = nullptr;       // host-evaluated start angles of the batch (start_mode 1)
+    double* h_start = nullptr;       // pinned staging for them
+    size_t cap_start = 0;
+    const double* next_start = nullptr;   // device array handed to the next launch (consumed by launch_optimize)
     unsigned char* d_stage = nullptr;
     size_t cap_stage = 0;
     int* d_work = nullptr;
@@ -248,6 +253,7 @@ void hpmvs_engine_destroy(hpmvs_engine_t* e) {
     cudaFree(e->d_pool_bq); cudaFree(e->d_pool_ctx);
     cudaFree(e->d_cams); cudaFree(e->d_covis_off); cudaFree(e->d_covis_ids);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_inccs); cudaFree(e->d_stage);
+    cudaFree(e->d_start); if (e->h_start) cudaFreeHost(e->h_start);
     cudaFree(e->d_work); cudaFree(e->d_counters);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
     cudaStreamDestroy(e->stream);
@@ -395,6 +401,33 @@ int hpmvs_engine_set_covis(hpmvs_engine_t* e, const int32_t* offsets, const int3
     return 0;
 }
 
+// parametersFromCenterNorm's two angles (src/hpmvs/PatchOptimizer.cpp:421-443) for every input patch with the HOST's libm:
+// std::asin(float), std::cos(double), std::acos(double) - the reference's own calls, so that the engine starts every
+// optimisation from exactly the reference's x[1], x[2] whatever libm the reference was linked against.
+static void host_start_parameters(hpmvs_engine* e, int n, const hpmvs_patch_t* in, double* out) {
+    const double lb = -23.99999, ub = 23.99999;                 // optimizePatch's bounds (:333-340)
+    const float angle_scale = (float)(M_PI / 48.0f);            // :398
+    for (int i = 0; i < n; i++) {
+        out[2 * i] = 0.0; out[2 * i + 1] = 0.0;
+        if (in[i].nimages < 1 || in[i].images[0] < 0 || in[i].images[0] >= e->ncams) continue;
+        const hp::DevCamera& cam = e->h_cams[in[i].images[0]];
+        const float* nn = in[i].normal;
+        const float fx = h_dot3(cam.nx, nn), fy = h_dot3(cam.ny, nn), fz = h_dot3(cam.nz, nn);
+        double x1, x2 = std::asin(fy);                            // float overload
+        const float cosb = std::cos(std::max(-1.0, std::min(1.0, x2)));
+        if (cosb == 0.0) x1 = 0.0;
+        else {
+            const double sina = fx / cosb;
+            const double cosa = -fz / cosb;
+            x1 = std::acos(std::min(1.0, std::max(-1.0, cosa)));
+            if (sina < 0.0) x1 = -x1;
+        }
+        x1 /= angle_scale; x2 /= angle_scale;
+        out[2 * i] = std::min(ub, std::max(lb, x1));
+        out[2 * i + 1] = std::min(ub, std::max(lb, x2));
+    }
+}
+
 static int launch_optimize(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, hpmvs_patch_t* d_out, cudaStream_t s) {
     int rc = check_ready(e);
     if (rc) return rc;
@@ -413,6 +446,8 @@ static int launch_optimize(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, hp
     if (lanes > V.lpw) lanes = V.lpw;
     if (e->force_lanes > 0) lanes = e->force_lanes;
     K.lanes_per_warp = lanes;
+    K.start = e->next_start;
+    e->next_start = nullptr;
     // more patches than resident slots -> parked variant (virtual slots per CTA, state pools in HBM/L2)
     const bool parked = e->parked_mode == 1 || (e->parked_mode != 0 && (long long)n > (long long)e->sm_count * V.ow * V.lpw * 5 / 4);
     HP_CUDA(cudaEventRecord(e->ev0, s));
@@ -453,6 +488,13 @@ int hpmvs_optimize_batch_device(hpmvs_engine_t* e, int n, const hpmvs_patch_t* d
     return launch_optimize(e, n, d_in, d_out, stream ? (cudaStream_t)stream : e->stream);
 }
 
+int hpmvs_engine_set_start_mode(hpmvs_engine_t* e, int mode) {
+    if (!e || (mode != 0 && mode != 1)) return HPMVS_E_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->start_mode = mode;
+    return 0;
+}
+
 int hpmvs_optimize_batch(hpmvs_engine_t* e, int n, const hpmvs_patch_t* in, hpmvs_patch_t* out, void* stream) {
     if (!e || n < 0 || (n > 0 && (!in || !out))) return HPMVS_E_ARG;
     if (n == 0) return 0;
@@ -470,6 +512,21 @@ int hpmvs_optimize_batch(hpmvs_engine_t* e, int n, const hpmvs_patch_t* in, hpmv
             if (in[i].images[j] < 0 || in[i].images[j] >= e->ncams) return HPMVS_E_ARG;
     }
     HP_CUDA(cudaMemcpyAsync(e->d_in, in, sizeof(hpmvs_patch_t) * n, cudaMemcpyHostToDevice, s));
+    if (e->start_mode == 1) {
+        // the one libm-dependent scalar step of the path, evaluated where the reference evaluates it: on the host
+        if ((size_t)n > e->cap_start) {
+            if (e->d_start) cudaFree(e->d_start);
+            if (e->h_start) cudaFreeHost(e->h_start);
+            e->d_start = nullptr; e->h_start = nullptr; e->cap_start = 0;
+            const size_t cap = (size_t)n + (size_t)n / 4 + 1024;
+            HP_CUDA(cudaMalloc(&e->d_start, cap * 2 * sizeof(double)));
+            HP_CUDA(cudaMallocHost(&e->h_start, cap * 2 * sizeof(double)));
+            e->cap_start = cap;
+        }
+        host_start_parameters(e, n, in, e->h_start);
+        HP_CUDA(cudaMemcpyAsync(e->d_start, e->h_start, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, s));
+        e->next_start = e->d_start;
+    }
     rc = launch_optimize(e, n, e->d_in, e->d_out, s);
     if (rc) return rc;
     HP_CUDA(cudaMemcpyAsync(out, e->d_out, sizeof(hpmvs_patch_t) * n, cudaMemcpyDeviceToHost, s));

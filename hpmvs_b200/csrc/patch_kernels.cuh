@@ -80,10 +80,13 @@ struct KParams {
     int* work_counter;
     unsigned long long* counters;   // patches, ok, evals, textures
     int lanes_per_warp;             // patches kept in flight per warp (1..32)
+    // optional: parametersFromCenterNorm's angles (x[1], x[2], scaled and clamped) per input patch, evaluated by the caller with
+    // the HOST's libm exactly where the reference evaluates them (PatchOptimizer.cpp:427-437); null = evaluate here
     // parked variant: per-CTA pools of virtual patch slots in HBM/L2 (state + context), `vslots` per CTA
     struct BqSlot* pool_bq;
     struct LaneCtx* pool_ctx;
     int vslots;
+    const double* start;            // see above (2 doubles per input patch) or null
 };
 
 struct ViewSetup {
@@ -708,6 +711,7 @@ __device__ __forceinline__ void init_parameters(LaneCtx& P, const KParams& K, co
     x[1] /= (double)K.angle_scale;
     x[2] /= (double)K.angle_scale;
     for (int i = 0; i < 3; i++) x[i] = fmin(ub[i], fmax(lb[i], x[i]));
+    if (K.start) { x[1] = K.start[2 * P.patch_index]; x[2] = K.start[2 * P.patch_index + 1]; }
 }
 
 // Scene::getColor(const Patch3d&) (Scene.cpp:300-327): lane = view; stable rank by colour norm
@@ -824,6 +828,12 @@ __device__ __forceinline__ void retire_patch(Scratch& W, LaneCtx& P, const KPara
 //     refinement).  Their hot loop is small and stays resident in the instruction cache.
 // Slots hand over through a per-slot state word in shared memory; patches come from a global atomic counter.
 // ----------------------------------------------------------------------------------------------------------
+#ifndef HP_SLEEP_Q
+#define HP_SLEEP_Q 64        // ns between polls of an idle sampler warp
+#endif
+#ifndef HP_SLEEP_OPT
+#define HP_SLEEP_OPT 200     // ns between polls of an optimizer warp waiting for its objectives
+#endif
 constexpr int QCAP = 1024;                // >= slots + sampler warps outstanding entries, power of two
 
 enum : int {
@@ -879,7 +889,7 @@ __device__ __forceinline__ int q_pop(QueueShared& C, int lane) {
     if (lane == 0) {
         const unsigned h = atomicAdd(&C.q_head, 1u);
         volatile int* q = &C.queue[h & (QCAP - 1)];
-        while ((e = *q) == 0) __nanosleep(64);
+        while ((e = *q) == 0) __nanosleep(HP_SLEEP_Q);
         *q = 0;
         __threadfence_block();
     }
@@ -946,7 +956,7 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
                 const unsigned dead = __ballot_sync(FULL, st == ST_DEAD);
                 if (dead == FULL) { st = -1; break; }
                 if (!waiting && ready) break;
-                __nanosleep(200);
+                __nanosleep(HP_SLEEP_OPT);
             }
             if (st == -1) break;
             __threadfence_block();
@@ -964,6 +974,7 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
                 const double f = *reinterpret_cast<volatile double*>(&C.fval[slot]);
                 const int act = bq3::advance(bq, f, xcur);
                 if (act == bq3::ASK) { set_center_norm(mine, K, xcur); st = ST_EVAL_PENDING; }
+                else if (act == bq3::YIELD) st = ST_EVAL_DONE;     // ready again next round, no objective needed
                 else st = ST_POSTING;
             } else {
                 st = 0;   // FILLING / POSTING / DEAD: nothing to do for this lane in this round
@@ -984,6 +995,7 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
             }
             if (st == ST_EVAL_PENDING) { st_state(my_state, ST_EVAL_PENDING); q_push(C.Q, REQ_EVAL, slot); }
             else if (st == ST_POSTING) { st_state(my_state, ST_POSTING); q_push(C.Q, REQ_POST, slot); }
+            // st == ST_EVAL_DONE (yield): the slot state is still ST_EVAL_DONE, it takes part in the next round as it is
             __syncwarp();
             t_adv += HP_CLOCK() - ta0;
         }
@@ -1173,6 +1185,7 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
                     act = bq3::advance(bq, f, xcur);
                 }
                 if (act == bq3::ASK) { set_center_norm(mine, K, xcur); st = ST_EVAL_PENDING; }
+                else if (act == bq3::YIELD) st = ST_EVAL_DONE;  // ready again next round, no objective needed
                 else {
                     st = ST_POSTING;
                     const int rc = bq.rc;                      // optimizePatch's epilogue (:364-381)
@@ -1201,7 +1214,7 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
             __syncwarp();
             if (lane < count) {
                 st_state(&C.sstate[slot], st);
-                q_push(C.Q, st == ST_EVAL_PENDING ? REQ_EVAL : REQ_POST, slot);
+                if (st != ST_EVAL_DONE) q_push(C.Q, st == ST_EVAL_PENDING ? REQ_EVAL : REQ_POST, slot);
             }
             __syncwarp();
             tw0 = HP_CLOCK();

@@ -71,6 +71,7 @@ def _lib():
         L.hpmvs_optimize_batch_device.argtypes = [vp, C.c_int, vp, vp, vp]
         L.hpmvs_ncc_batch.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, fp, vp]
         L.hpmvs_ncc_batch_device.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, vp]
+        L.hpmvs_engine_set_start_mode.argtypes = [vp, C.c_int]
         L.hpmvs_engine_counters.argtypes = [vp, C.POINTER(Counters), C.c_int]
         L.hpmvs_engine_stream.argtypes = [vp]; L.hpmvs_engine_stream.restype = vp
         L.hpmvs_engine_last_kernel_ms.argtypes = [vp]; L.hpmvs_engine_last_kernel_ms.restype = C.c_float
@@ -213,6 +214,11 @@ class Engine:
             out = np.empty_like(patches)
         _check(_lib().hpmvs_optimize_batch(self._h, len(patches), patches.ctypes.data, out.ctypes.data, stream or None))
         return out
+
+    def set_start_mode(self, host_libm: bool) -> None:
+        """True: optimize() evaluates parametersFromCenterNorm's asin/cos/acos on the host with this machine's libm, like
+        the reference (bit-identical to a reference built here); False (default): on the device, asin correctly rounded."""
+        _check(_lib().hpmvs_engine_set_start_mode(self._h, 1 if host_libm else 0))
 
     def optimize_ptr(self, n: int, in_ptr: int, out_ptr: int, stream: int = 0) -> None:
         """Same, on raw host pointers (e.g. pinned torch tensors)."""

@@ -132,6 +132,15 @@ int  hpmvs_engine_set_covis(hpmvs_engine_t *e, const int32_t *offsets, const int
  * stream has been synchronised. */
 int  hpmvs_optimize_batch(hpmvs_engine_t *e, int n, const hpmvs_patch_t *in, hpmvs_patch_t *out, void *stream);
 
+/* Where the one libm-dependent scalar step of the path is evaluated: parametersFromCenterNorm's starting angles
+ * std::asin(float) / std::cos / std::acos (src/hpmvs/PatchOptimizer.cpp:427-437).
+ *   mode 0 (default): on the device, asin correctly rounded (= a reference linked against a correctly rounded libm);
+ *   mode 1: hpmvs_optimize_batch() evaluates them on the HOST with the caller's libm - the reference's own calls in the
+ *           reference's own place - and hands them to the kernel, so that results are bit-identical to a reference built
+ *           on the same machine (glibc 2.39's asinf is not correctly rounded).  Costs ~60 ns of host time per patch.
+ * The device-resident call always uses mode 0. */
+int  hpmvs_engine_set_start_mode(hpmvs_engine_t *e, int mode);
+
 /* Same work on device-resident records (no copies, asynchronous on `stream`). */
 int  hpmvs_optimize_batch_device(hpmvs_engine_t *e, int n, const hpmvs_patch_t *d_in, hpmvs_patch_t *d_out,
                                  void *stream);

@@ -64,6 +64,8 @@ public:
         hpmvs_engine_t* e = nullptr;
         check(hpmvs_engine_create(&o, device, &e), "hpmvs_engine_create");
         engine_.reset(e);
+        // drop-in fidelity: the start angles are evaluated with the host's libm, as the reference does (PatchOptimizer.cpp:427-437)
+        check(hpmvs_engine_set_start_mode(e, 1), "hpmvs_engine_set_start_mode");
     }
     hpmvs_engine_t* engine() const { return engine_.get(); }
 
