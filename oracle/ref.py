@@ -21,6 +21,7 @@ from . import Camera, Options, PATCH_DTYPE, _p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libhpmvs_ref.so")
 BIN_PATH = os.path.join(_HERE, "_ref", "hpmvs_ref")
+DROPIN_BIN_PATH = os.path.join(_HERE, "_ref", "hpmvs_ref_b200")   # same CLI, integration/PatchOptimizer_b200.cpp instead of PatchOptimizer.cpp
 REF_ROOT = "/root/reference"
 FAIL = 100   # status of a patch for which the reference's optimize() returned false
 
@@ -34,6 +35,9 @@ def build() -> Optional[str]:
     if os.path.isdir(os.path.join(REF_ROOT, "src", "hpmvs")):
         subprocess.run(["make", "-C", _HERE, "ref", "-j8"], check=True, capture_output=True)
         subprocess.run(["make", "-C", _HERE, "refhpmvs", "-j8"], check=True, capture_output=True)
+        if os.path.exists(os.path.join(_HERE, "..", "hpmvs_b200", "libhpmvs_b200.so")):
+            # the reference's CLI linked against the engine instead of its own PatchOptimizer.cpp (integration/)
+            subprocess.run(["make", "-C", _HERE, "dropin"], check=True, capture_output=True)
     return LIB_PATH if available() else None
 
 
@@ -166,7 +170,9 @@ class RefScene:
         return out
 
 
-def run_cli(nvm_path: str, outdir: str, threads: int = 1, extra=()) -> subprocess.CompletedProcess:
-    """The reference's own command line (src/main.cpp): hpmvs --nvm=... --outdir=..."""
+def run_cli(nvm_path: str, outdir: str, threads: int = 1, extra=(), dropin: bool = False, monotone_heap: bool = False) -> subprocess.CompletedProcess:
+    """The reference's own command line (src/main.cpp): hpmvs --nvm=... --outdir=...; dropin=True runs the build whose
+    PatchOptimizer is the B200 engine (needs a GPU); monotone_heap=True runs the *_det builds (oracle/ref_monotone_new.cpp)."""
     env = dict(os.environ, OMP_NUM_THREADS=str(threads))
-    return subprocess.run([BIN_PATH, f"--nvm={nvm_path}", f"--outdir={outdir}", *extra], env=env, capture_output=True, text=True)
+    exe = (DROPIN_BIN_PATH if dropin else BIN_PATH) + ("_det" if monotone_heap else "")
+    return subprocess.run([exe, f"--nvm={nvm_path}", f"--outdir={outdir}", *extra], env=env, capture_output=True, text=True)

@@ -93,3 +93,55 @@ def test_ext_ply_binary_and_light(tmp_path):
     # empty set
     hio.write_ext_ply(path, np.zeros(0, hp.PATCH_DTYPE))
     assert "element vertex 0" in open(path).read()
+
+
+def _parse_ext_ply_ascii(path):
+    """ext-PLY (ascii) as DynOctTree::toExtPly writes it (doctree.h:525-622) -> patch records."""
+    lines = open(path).read().split("\n")
+    n = int([l for l in lines if l.startswith("element vertex")][0].split()[2])
+    h = lines.index("end_header") + 1
+    rec = np.zeros(n, hp.PATCH_DTYPE)
+    for i in range(n):
+        f = lines[h + i].split()
+        rec["center"][i, :3] = [np.float32(v) for v in f[0:3]]; rec["center"][i, 3] = 1
+        rec["normal"][i, :3] = [np.float32(v) for v in f[3:6]]
+        rec["color"][i] = [float(v) for v in f[6:9]]
+        rec["scale"][i] = np.float32(f[9])
+        g = lines[h + n + i].split()
+        k = int(g[0]); rec["nimages"][i] = k; rec["images"][i, :k] = [int(v) for v in g[1:1 + k]]
+    return rec
+
+
+def test_ext_ply_writer_reproduces_the_reference_cli_file(tmp_path):
+    # tests/golden/ref_cli_patches-40.ply was written by the REFERENCE'S OWN command line (oracle/_ref/hpmvs_ref_det, built from
+    # /root/reference/src where it lies) on plane_scene(n_views=5, 320x240, f=300, 60 seeds, seed 13): the level-40 dump.
+    # Our writer must produce the same bytes from the same records (format, number formatting, visibility lists).
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_cli_patches-40.ply")
+    rec = _parse_ext_ply_ascii(gold)
+    assert len(rec) == 268
+    out = str(tmp_path / "ours.ply")
+    hio.write_ext_ply(out, rec, binary=False)
+    assert open(out, "rb").read() == open(gold, "rb").read()
+
+
+def test_reference_cli_reads_our_nvm_and_its_ply_round_trips(tmp_path):
+    from oracle import ref
+    if not os.path.exists(ref.BIN_PATH):
+        import pytest
+        pytest.skip("oracle/_ref/hpmvs_ref not built (needs /root/reference)")
+    sc = hp.synth.plane_scene(n_views=4, width=320, height=240, focal=300.0, n_seeds=80, seed=17, tex_size=256)
+    nvm = str(tmp_path / "scene.nvm")
+    hp.synth.write_nvm(sc, nvm)                                     # our NVM_V3 + PPM writer ...
+    r = ref.run_cli(nvm, str(tmp_path / "out"), threads=2, extra=["--light_output=1"])   # ... read by the reference's NVMReader / CImg
+    assert r.returncode == 0, r.stderr[-1000:]
+    final = str(tmp_path / "out" / "patches-final.ply")
+    rec = _parse_ext_ply_ascii(final)
+    assert len(rec) > 100 and (rec["nimages"] >= 2).all()
+    ours = str(tmp_path / "ours.ply")
+    hio.write_ext_ply(ours, rec, binary=False)
+    assert open(ours, "rb").read() == open(final, "rb").read()
+    # the binary "light" variant: same header, same size
+    light = open(str(tmp_path / "out" / "patches-final-light.ply"), "rb").read()
+    hio.write_ext_ply(str(tmp_path / "ours_light.ply"), rec, binary=True, normal=False, scale=False, visibility=False)
+    mine = open(str(tmp_path / "ours_light.ply"), "rb").read()
+    assert light[:light.index(b"end_header")] == mine[:mine.index(b"end_header")] and len(light) == len(mine)
