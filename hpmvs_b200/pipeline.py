@@ -65,7 +65,16 @@ def _pack(keys: np.ndarray) -> np.ndarray:
 
 
 class WavefrontDriver:
-    def __init__(self, backend, origin, root_width: float, start_level: int, final_level: int, max_rounds: int = 64):
+    def __init__(self, backend, origin, root_width: float, start_level: int, final_level: int, max_rounds: int = 64,
+                 final_min_level: int = 9, cameras=None):
+        # final_min_level = HpmvsOptions::PATCH_FINAL_MINLEVEL as the CLI sets it (src/main.cpp:44,234): a cell below that tree
+        # level whose patch yields no child when it branches is split anyway and loses its patch (CellProcessor.cpp:266-283)
+        self.final_min_level = final_min_level
+        # cameras (hpmvs_camera_t list, optional): enables the per-round image-space de-duplication below
+        self.P0 = None
+        if cameras is not None:
+            self.P0 = np.stack([np.ctypeslib.as_array(c.P)[0].astype(np.float64) for c in cameras])     # [ncams, 3, 4]
+            self.k00 = np.array([c.k00 for c in cameras], np.float64)
         self.b = backend
         self.origin = np.asarray(origin, np.float64)
         self.root_width = float(root_width)
@@ -95,6 +104,24 @@ class WavefrontDriver:
                 level_cells[k] = rec[i].copy()
                 live[i] = True
         return live
+
+    def _first_per_ref_pixel(self, rec: np.ndarray, width: float) -> np.ndarray:
+        """The reference commits one patch at a time, so a patch that has just been accepted occupies its depth-map pixels and blocks
+        the next candidate that lands on them (pixelFreeTests, Scene.cpp:587-611).  A batched round tests all candidates against the
+        SAME snapshot; to keep the one-patch-per-image-cell behaviour the accepted candidates of a round are thinned to the first one
+        per cell of their reference view, a cell being the image footprint of one tree cell (width * f / depth pixels)."""
+        if self.P0 is None or len(rec) == 0:
+            return np.ones(len(rec), bool)
+        ref = rec["images"][:, 0].astype(np.int64)
+        X = rec["center"].astype(np.float64)
+        r = np.einsum("nij,nj->ni", self.P0[ref], X)
+        z = np.maximum(r[:, 2], 1e-9)
+        cell_px = np.maximum(width * self.k00[ref] / z, 1e-6)
+        ku = np.floor(r[:, 0] / z / cell_px).astype(np.int64); kv = np.floor(r[:, 1] / z / cell_px).astype(np.int64)
+        key = (ref << 44) | ((ku + (1 << 20)) << 22) | (kv + (1 << 20))
+        _, firsts = np.unique(key, return_index=True)
+        keep = np.zeros(len(rec), bool); keep[firsts] = True
+        return keep
 
     # -- the loop -----------------------------------------------------------------------------------------
     def run(self, seeds: np.ndarray) -> np.ndarray:
@@ -131,6 +158,10 @@ class WavefrontDriver:
                 good &= (res["scale"] * 2.0 < w) & (res["scale"] * 2.0 > w / 2.0)
                 drift = np.linalg.norm(res["center"][:, :3] - frontier["center"][parent][:, :3], axis=1)
                 good &= drift < w * 1.5
+                # a patch that leaves the root cube is handed to the neighbouring sub-tree, and dropped when there is none
+                # (CellProcessor.cpp:147-153, distributeBorderCell :533-540): the cloud never grows beyond the octree's root
+                rel = (res["center"][:, :3].astype(np.float64) - self.origin) / self.root_width
+                good &= ((rel >= 0.0) & (rel < 1.0)).all(axis=1)
                 t = time.perf_counter()
                 counts = self.b.accept(res, DEPTH_TEST_FACTOR)
                 self.stats.seconds_accept += time.perf_counter() - t
@@ -138,6 +169,7 @@ class WavefrontDriver:
                 good &= (counts[:, 0] >= MIN_IMAGES) & (counts[:, 1] < MIN_IMAGES)
                 good &= (counts[:, 2] >= MIN_IMAGES - 1) & (counts[:, 2] * 1.0 / nimg > 0.75)
                 acc = res[good]
+                acc = acc[self._first_per_ref_pixel(acc, w)]
                 if len(acc) == 0:
                     break
                 live = self._insert(cells, acc, w)
@@ -160,9 +192,10 @@ class WavefrontDriver:
             keep = (res["status"] == 0) & (_pack(_cell_keys(res["center"], self.origin, w)) == pkeys) if len(cand) else np.zeros(0, bool)
             children = res[keep]
             branched_parents = np.unique(parent[keep]) if len(cand) else np.zeros(0, np.int64)
-            # cells that did not branch keep their patch as a final result (CellProcessor.cpp:266-269)
+            # cells that did not branch keep their patch as a final result - from PATCH_FINAL_MINLEVEL on (CellProcessor.cpp:266-269)
             stay = np.ones(len(patches), bool); stay[branched_parents] = False
-            final.append(patches[stay])
+            if level >= self.final_min_level:
+                final.append(patches[stay])
             self.stats.per_level.append((level, n_ext, int(len(children))))
             cells = {}
             level += 1

@@ -17,7 +17,7 @@ eng = hp.Engine.from_synth(sc)
 seeds, valid = hp.seed_patches(eng.options, eng.cameras, sc.points, sc.meas_offsets, sc.meas_cam)
 seeds = np.ascontiguousarray(seeds[valid])
 width0 = float(np.median(seeds["scale"])) * 2.2
-args = dict(origin=(-16.0, -16.0, -16.0), root_width=width0 * 4, start_level=2, final_level=5)
+args = dict(origin=(-16.0, -16.0, -16.0), root_width=width0 * 512, start_level=9, final_level=12, final_min_level=0)   # root cube covers the scene
 res = {}
 for name in ("gpu", "cpu"):
     if name == "gpu":
@@ -40,7 +40,7 @@ matched = len(kg & kc)
 from hpmvs_b200 import io as hio
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 hio.write_ext_ply(os.path.join(ROOT, "gpurun_out", "patches-final.ply"), res["gpu_out"], binary=True)
-print(json.dumps({"workload": "11-view 3072x2048 synthetic plane, %d seeds, levels 2..5, level-synchronous driver" % len(seeds),
+print(json.dumps({"workload": "11-view 3072x2048 synthetic plane, %d seeds, 4 tree levels, level-synchronous driver" % len(seeds),
                   "host_threads_cpu_backend": len(os.sched_getaffinity(0)), "identical_patch_sets": bool(same),
                   "bit_identical_patches": matched, "bit_identical_fraction_of_gpu_set": matched / max(1, len(g)),
                   "gpu": {k: v for k, v in res["gpu"].items()}, "cpu": {k: v for k, v in res["cpu"].items()},

@@ -59,7 +59,8 @@ def test_pipeline_same_patch_set_on_engine_and_oracle():
     seeds, valid = hp.seed_patches(eng.options, eng.cameras, sc.points, sc.meas_offsets, sc.meas_cam)
     seeds = np.ascontiguousarray(seeds[valid])
     width0 = float(np.median(seeds["scale"])) * 2.2          # seed cells: 2*scale < width
-    args = dict(origin=(-8.0, -8.0, -8.0), root_width=width0 * 4, start_level=2, final_level=4)
+    # root cube [-8, -8 + 64*width0)^3 covers the scene (patches that leave the root are dropped, as in the reference)
+    args = dict(origin=(-8.0, -8.0, -8.0), root_width=width0 * 64, start_level=6, final_level=8, final_min_level=0)
     oracle.set_cr_asinf(True)
     try:
         d_ref = pipeline.WavefrontDriver(OracleBackend(orc), **args)
