@@ -1,0 +1,223 @@
+// Level-synchronous host driver of the expand -> optimize -> filter loop around the engine, in C++ behind the C ABI
+// (hpmvs_pipeline_run, include/hpmvs_b200.h).  It is the batching stand-in for the reference's scheduler
+// (CellProcessor + DynOctTree, /root/reference/src/hpmvs/CellProcessor.cpp:369-420, src/main.cpp:145-155): per tree level it
+// collects the candidates of ALL cells, optimises them in one engine batch, runs the acceptance tests against a snapshot of the
+// depth maps and commits the survivors in a deterministic order.  Kept from the reference, per cell:
+//   seeds   reject when the optimised centre moved more than 2*scale (Scene.cpp:171); one patch per cell, the better supported
+//           patch wins (CellProcessor::filter, CellProcessor.cpp:43-82)
+//   extend  6 candidates one cell width away, scale = width*0.9/2 (CellProcessor.cpp:98-119); accepted when width/2 < 2*scale < width,
+//           drift < 1.5*width, depthTests >= MIN_IMAGES, viewBlockTest < MIN_IMAGES, pixelFreeTests >= MIN_IMAGES-1 and > 75 % of the
+//           views (:129-142); a patch that leaves the root cube is dropped (:147-153, :533-540)
+//   branch  4 candidates at width/4, scale = width*0.45/2, kept when they stay inside the parent's cell (:227-264); a cell that
+//           yields no child keeps its patch from PATCH_FINAL_MINLEVEL on, below that it loses it (:266-283)
+// hpmvs_b200/pipeline.py is the same algorithm in numpy against a backend protocol (it also runs on the CPU oracle);
+// tests/test_pipeline.py requires identical patch arrays from both.
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <chrono>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "../../include/hpmvs_b200.h"
+
+namespace {
+
+typedef std::vector<hpmvs_patch_t> Recs;
+const int MIN_IMAGES = 3;
+const float DEPTH_TEST_FACTOR = 1.0f;
+
+struct Driver {
+    hpmvs_engine_t* e;
+    const hpmvs_pipeline_params_t* p;
+    hpmvs_pipeline_stats_t st;
+    double origin[3];
+
+    double width(int level) const { return p->root_width / (double)(1 << level); }
+
+    int64_t key_of(const float* c, double w) const {
+        int64_t k[3];
+        for (int i = 0; i < 3; i++) k[i] = (int64_t)std::floor(((double)c[i] - origin[i]) / w) + ((int64_t)1 << 20);
+        return (k[0] << 42) | (k[1] << 21) | k[2];
+    }
+
+    int optimize(Recs& r) {
+        if (r.empty()) return 0;
+        const auto t0 = std::chrono::steady_clock::now();
+        const int rc = hpmvs_optimize_batch(e, (int)r.size(), r.data(), r.data(), nullptr);
+        st.seconds_optimize += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        st.optimize_calls += (int64_t)r.size();
+        for (const hpmvs_patch_t& q : r) st.optimized_ok += (q.status == HPMVS_OK);
+        return rc;
+    }
+
+    // one patch per cell; on a collision the patch with more views wins, then the earlier one.  `cells` keeps insertion order.
+    void insert(Recs& cells, std::unordered_map<int64_t, int>& index, const Recs& rec, double w, std::vector<char>* live) {
+        if (live) live->assign(rec.size(), 0);
+        for (size_t i = 0; i < rec.size(); i++) {
+            const int64_t k = key_of(rec[i].center, w);
+            auto it = index.find(k);
+            if (it == index.end()) { index[k] = (int)cells.size(); cells.push_back(rec[i]); if (live) (*live)[i] = 1; }
+            else if (rec[i].nimages > cells[it->second].nimages) { cells[it->second] = rec[i]; if (live) (*live)[i] = 1; }
+        }
+    }
+
+    static float norm3f(const float* a, const float* b) {
+        const float d0 = a[0] - b[0], d1 = a[1] - b[1], d2 = a[2] - b[2];
+        return std::sqrt((d0 * d0 + d1 * d1) + d2 * d2);
+    }
+
+    // the accepted candidates of one round thinned to the first one per image cell of their reference view (see pipeline.py)
+    void first_per_ref_pixel(const Recs& rec, double w, std::vector<char>& keep) const {
+        keep.assign(rec.size(), 1);
+        if (!p->dedup_ref_pixel) return;
+        std::unordered_set<int64_t> seen;
+        for (size_t i = 0; i < rec.size(); i++) {
+            const int ref = rec[i].images[0];
+            const hpmvs_camera_t& cam = p->cams[ref];
+            double r[3];
+            for (int a = 0; a < 3; a++)
+                r[a] = (((double)cam.P[0][a][0] * (double)rec[i].center[0] + (double)cam.P[0][a][1] * (double)rec[i].center[1]) +
+                        (double)cam.P[0][a][2] * (double)rec[i].center[2]) + (double)cam.P[0][a][3] * (double)rec[i].center[3];
+            const double z = r[2] > 1e-9 ? r[2] : 1e-9;
+            double cell_px = w * (double)cam.k00 / z;
+            if (!(cell_px > 1e-6)) cell_px = 1e-6;
+            const int64_t ku = (int64_t)std::floor(r[0] / z / cell_px), kv = (int64_t)std::floor(r[1] / z / cell_px);
+            const int64_t key = ((int64_t)ref << 44) | ((ku + ((int64_t)1 << 20)) << 22) | (kv + ((int64_t)1 << 20));
+            if (!seen.insert(key).second) keep[i] = 0;
+        }
+    }
+
+    int run(const Recs& seeds, Recs& final_out) {
+        int rc;
+        if ((rc = hpmvs_engine_depth_reset(e)) < 0) return rc;
+        Recs out = seeds;
+        if ((rc = optimize(out)) < 0) return rc;
+        Recs first;
+        for (size_t i = 0; i < out.size(); i++) {
+            if (out[i].status != HPMVS_OK) continue;
+            if (norm3f(out[i].center, seeds[i].center) > out[i].scale * 2) continue;             // Scene.cpp:171
+            first.push_back(out[i]);
+        }
+        Recs cells;
+        std::unordered_map<int64_t, int> index;
+        int level = p->start_level;
+        insert(cells, index, first, width(level), nullptr);
+        if ((rc = hpmvs_depth_set_batch(e, (int)cells.size(), cells.data(), nullptr)) < 0) return rc;
+        std::vector<char> live, keep;
+        std::vector<float> widths;
+        std::vector<int32_t> counts;
+        for (;;) {
+            const double w = width(level);
+            Recs frontier = cells;
+            int64_t n_ext = 0;
+            for (int round = 0; round < p->max_rounds && !frontier.empty(); round++) {        // extend until the wavefront dies out
+                Recs cand(frontier.size() * 6);
+                widths.assign(frontier.size(), (float)w);
+                if ((rc = hpmvs_expand_candidates(p->ncams, p->cams, (int)frontier.size(), frontier.data(), widths.data(), 6, cand.data())) < 0) return rc;
+                // one candidate per free cell and round (first parent wins), like a cell being filled once
+                std::unordered_set<int64_t> seen;
+                Recs sel; std::vector<int> parent;
+                for (size_t i = 0; i < cand.size(); i++) {
+                    const int64_t k = key_of(cand[i].center, w);
+                    const bool uniq = seen.insert(k).second;
+                    if (uniq && index.find(k) == index.end()) { sel.push_back(cand[i]); parent.push_back((int)(i / 6)); }
+                }
+                if (sel.empty()) break;
+                if ((rc = optimize(sel)) < 0) return rc;
+                counts.assign(sel.size() * 3, 0);
+                const auto t0 = std::chrono::steady_clock::now();
+                if ((rc = hpmvs_accept_batch(e, (int)sel.size(), sel.data(), DEPTH_TEST_FACTOR, counts.data(), nullptr)) < 0) return rc;
+                st.seconds_accept += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                Recs acc;
+                for (size_t i = 0; i < sel.size(); i++) {
+                    const hpmvs_patch_t& r = sel[i];
+                    bool good = r.status == HPMVS_OK;
+                    good = good && (r.scale * 2.0f < (float)w) && (r.scale * 2.0f > (float)(w / 2.0));
+                    good = good && norm3f(r.center, frontier[parent[i]].center) < (float)(w * 1.5);
+                    for (int a = 0; a < 3 && good; a++) {
+                        const double rel = ((double)r.center[a] - origin[a]) / p->root_width;
+                        good = rel >= 0.0 && rel < 1.0;
+                    }
+                    const int nimg = r.nimages > 1 ? r.nimages : 1;
+                    good = good && counts[3 * i] >= MIN_IMAGES && counts[3 * i + 1] < MIN_IMAGES;
+                    good = good && counts[3 * i + 2] >= MIN_IMAGES - 1 && (counts[3 * i + 2] * 1.0 / nimg > 0.75);
+                    if (good) acc.push_back(r);
+                }
+                first_per_ref_pixel(acc, w, keep);
+                Recs acc2;
+                for (size_t i = 0; i < acc.size(); i++) if (keep[i]) acc2.push_back(acc[i]);
+                if (acc2.empty()) break;
+                insert(cells, index, acc2, w, &live);
+                Recs fresh;
+                for (size_t i = 0; i < acc2.size(); i++) if (live[i]) fresh.push_back(acc2[i]);
+                if ((rc = hpmvs_depth_set_batch(e, (int)fresh.size(), fresh.data(), nullptr)) < 0) return rc;
+                n_ext += (int64_t)fresh.size();
+                frontier.swap(fresh);
+            }
+            const Recs& patches = cells;
+            if (st.nlevels < HPMVS_PIPELINE_MAX_LEVELS) { st.level[st.nlevels] = level; st.extended[st.nlevels] = n_ext; st.branched[st.nlevels] = 0; }
+            if (level >= p->final_level || patches.empty()) {
+                final_out.insert(final_out.end(), patches.begin(), patches.end());
+                if (st.nlevels < HPMVS_PIPELINE_MAX_LEVELS) st.nlevels++;
+                break;
+            }
+            // branch into the next level: 4 candidates per patch, kept when they stay inside the parent's cell
+            Recs cand4(patches.size() * 4);
+            widths.assign(patches.size(), (float)w);
+            if ((rc = hpmvs_expand_candidates(p->ncams, p->cams, (int)patches.size(), patches.data(), widths.data(), 4, cand4.data())) < 0) return rc;
+            Recs cand; std::vector<int> parent; std::vector<int64_t> pkeys;
+            for (size_t i = 0; i < cand4.size(); i++) {
+                const int64_t pk = key_of(patches[i / 4].center, w);
+                if (key_of(cand4[i].center, w) == pk) { cand.push_back(cand4[i]); parent.push_back((int)(i / 4)); pkeys.push_back(pk); }
+            }
+            if ((rc = optimize(cand)) < 0) return rc;
+            Recs children;
+            std::vector<char> branched(patches.size(), 0);
+            for (size_t i = 0; i < cand.size(); i++)
+                if (cand[i].status == HPMVS_OK && key_of(cand[i].center, w) == pkeys[i]) { children.push_back(cand[i]); branched[parent[i]] = 1; }
+            if (level >= p->final_min_level)
+                for (size_t i = 0; i < patches.size(); i++) if (!branched[i]) final_out.push_back(patches[i]);
+            if (st.nlevels < HPMVS_PIPELINE_MAX_LEVELS) { st.branched[st.nlevels] = (int64_t)children.size(); st.nlevels++; }
+            Recs next; std::unordered_map<int64_t, int> nindex;
+            level += 1;
+            insert(next, nindex, children, width(level), nullptr);
+            cells.swap(next); index.swap(nindex);
+            if ((rc = hpmvs_depth_set_batch(e, (int)cells.size(), cells.data(), nullptr)) < 0) return rc;
+        }
+        return 0;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int hpmvs_pipeline_run(hpmvs_engine_t* e, const hpmvs_pipeline_params_t* params, int nseeds, const hpmvs_patch_t* seeds,
+                       hpmvs_patch_t** out, int* nout, hpmvs_pipeline_stats_t* stats) {
+    if (!e || !params || !out || !nout || nseeds < 0 || (nseeds > 0 && !seeds) || !params->cams || params->ncams <= 0 ||
+        params->start_level < 0 || params->final_level < params->start_level || params->final_level > 20 || !(params->root_width > 0.0))
+        return HPMVS_E_ARG;
+    Driver d;
+    d.e = e; d.p = params;
+    std::memset(&d.st, 0, sizeof(d.st));
+    for (int i = 0; i < 3; i++) d.origin[i] = params->origin[i];
+    Recs s(seeds, seeds + nseeds), fin;
+    const int rc = d.run(s, fin);
+    if (stats) *stats = d.st;
+    if (rc < 0) return rc;
+    *nout = (int)fin.size();
+    *out = nullptr;
+    if (!fin.empty()) {
+        *out = (hpmvs_patch_t*)std::malloc(sizeof(hpmvs_patch_t) * fin.size());
+        if (!*out) return HPMVS_E_ARG;
+        std::memcpy(*out, fin.data(), sizeof(hpmvs_patch_t) * fin.size());
+    }
+    return 0;
+}
+
+void hpmvs_free(void* p) { std::free(p); }
+
+}  // extern "C"

@@ -114,7 +114,8 @@ class WavefrontDriver:
             return np.ones(len(rec), bool)
         ref = rec["images"][:, 0].astype(np.int64)
         X = rec["center"].astype(np.float64)
-        r = np.einsum("nij,nj->ni", self.P0[ref], X)
+        P = self.P0[ref]
+        r = ((P[:, :, 0] * X[:, 0:1] + P[:, :, 1] * X[:, 1:2]) + P[:, :, 2] * X[:, 2:3]) + P[:, :, 3] * X[:, 3:4]   # fixed order (host_pipeline.cpp)
         z = np.maximum(r[:, 2], 1e-9)
         cell_px = np.maximum(width * self.k00[ref] / z, 1e-6)
         ku = np.floor(r[:, 0] / z / cell_px).astype(np.int64); kv = np.floor(r[:, 1] / z / cell_px).astype(np.int64)
@@ -202,3 +203,42 @@ class WavefrontDriver:
             self._insert(cells, children, self.width(level))
             self.b.depth_set(np.array(list(cells.values()), dtype=self.b.dtype) if cells else children[:0])
         return np.concatenate(final) if final else seeds[:0]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The same driver in C++ behind the C ABI (hpmvs_pipeline_run, hpmvs_b200/csrc/host_pipeline.cpp): the product's host path.
+# ----------------------------------------------------------------------------------------------------------------------
+def run_native(engine, seeds: np.ndarray, origin, root_width: float, start_level: int, final_level: int, final_min_level: int = 9,
+               max_rounds: int = 64, dedup_ref_pixel: bool = True):
+    """Runs hpmvs_pipeline_run on `engine`; returns (final patch records, PipelineStats)."""
+    import ctypes as C
+    from . import engine as E
+    L = E._lib()
+
+    class Params(C.Structure):
+        _fields_ = [("origin", C.c_double * 3), ("root_width", C.c_double), ("start_level", C.c_int32), ("final_level", C.c_int32),
+                    ("final_min_level", C.c_int32), ("max_rounds", C.c_int32), ("dedup_ref_pixel", C.c_int32), ("ncams", C.c_int32),
+                    ("cams", C.POINTER(E.Camera))]
+
+    class Stats(C.Structure):
+        _fields_ = [("optimize_calls", C.c_int64), ("optimized_ok", C.c_int64), ("seconds_optimize", C.c_double), ("seconds_accept", C.c_double),
+                    ("nlevels", C.c_int32), ("level", C.c_int32 * 24), ("extended", C.c_int64 * 24), ("branched", C.c_int64 * 24)]
+
+    cams = (E.Camera * len(engine.cameras))(*engine.cameras)
+    prm = Params((C.c_double * 3)(*[float(v) for v in origin]), float(root_width), start_level, final_level, final_min_level, max_rounds,
+                 1 if dedup_ref_pixel else 0, len(engine.cameras), cams)
+    st = Stats()
+    s = np.ascontiguousarray(seeds)
+    assert s.dtype == E.PATCH_DTYPE
+    out_p = C.c_void_p(); n = C.c_int32()
+    L.hpmvs_pipeline_run.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(Stats)]
+    L.hpmvs_free.argtypes = [C.c_void_p]
+    E._check(L.hpmvs_pipeline_run(engine._h, C.byref(prm), len(s), s.ctypes.data, C.byref(out_p), C.byref(n), C.byref(st)))
+    try:
+        buf = (C.c_char * (n.value * E.PATCH_DTYPE.itemsize)).from_address(out_p.value) if n.value else b""
+        out = np.frombuffer(buf, dtype=E.PATCH_DTYPE, count=n.value).copy() if n.value else np.zeros(0, E.PATCH_DTYPE)
+    finally:
+        L.hpmvs_free(out_p)
+    ps = PipelineStats(int(st.optimize_calls), int(st.optimized_ok), float(st.seconds_optimize), float(st.seconds_accept),
+                       [(int(st.level[i]), int(st.extended[i]), int(st.branched[i])) for i in range(st.nlevels)])
+    return out, ps

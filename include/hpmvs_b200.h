@@ -172,6 +172,34 @@ int  hpmvs_engine_download_depth(hpmvs_engine_t *e, int cam, int level, float *o
 int  hpmvs_expand_candidates(int ncams, const hpmvs_camera_t *cams, int n, const hpmvs_patch_t *parents,
                              const float *widths, int mode, hpmvs_patch_t *out);
 
+/* ---- the loop around the path: level-synchronous expand -> optimize -> filter driver (host C++, hpmvs_b200/csrc/host_pipeline.cpp) ----
+ * Batching stand-in for the reference's scheduler (CellProcessor::processQueue + DynOctTree, src/main.cpp:145-155): per octree level
+ * all candidates of all cells go through ONE hpmvs_optimize_batch / hpmvs_accept_batch.  See the file header for what is kept. */
+#define HPMVS_PIPELINE_MAX_LEVELS 24
+typedef struct hpmvs_pipeline_params {
+    double  origin[3];             /* low corner of the octree's root cube (Scene.cpp:186-193: centre - width/2) */
+    double  root_width;            /* its edge length; cells of tree level L are root_width / 2^L wide */
+    int32_t start_level;           /* level the accepted seeds are inserted at */
+    int32_t final_level;           /* last level (inclusive) */
+    int32_t final_min_level;       /* HpmvsOptions::PATCH_FINAL_MINLEVEL (9 from the CLI, src/main.cpp:44,234) */
+    int32_t max_rounds;            /* extension rounds per level (64) */
+    int32_t dedup_ref_pixel;       /* != 0: one accepted candidate per reference-view image cell and round */
+    int32_t ncams;
+    const hpmvs_camera_t *cams;    /* the cameras the engine was given (candidate construction runs on the host) */
+} hpmvs_pipeline_params_t;
+typedef struct hpmvs_pipeline_stats {
+    int64_t optimize_calls, optimized_ok;
+    double  seconds_optimize, seconds_accept;
+    int32_t nlevels;
+    int32_t level[HPMVS_PIPELINE_MAX_LEVELS];
+    int64_t extended[HPMVS_PIPELINE_MAX_LEVELS], branched[HPMVS_PIPELINE_MAX_LEVELS];
+} hpmvs_pipeline_stats_t;
+/* seeds: candidate patches as hpmvs_seed_patches() builds them.  *out receives a malloc'ed array of *nout final patches
+ * (release with hpmvs_free).  Resets the engine's depth maps first. */
+int  hpmvs_pipeline_run(hpmvs_engine_t *e, const hpmvs_pipeline_params_t *params, int nseeds, const hpmvs_patch_t *seeds,
+                        hpmvs_patch_t **out, int *nout, hpmvs_pipeline_stats_t *stats);
+void hpmvs_free(void *p);
+
 /* ---- host-side scene surface (plain C++ on the host, no GPU needed): what feeds the engine ---- */
 
 /* Replaces mo3d::Camera::init (src/hpmvs/Camera.cpp:34-81) for one NVM camera line

@@ -62,11 +62,15 @@ mn, mx = c.min(0), c.max(0)
 width = float((mx - mn).max())
 origin = (mn + mx) / 2.0 - width / 2.0
 t1 = time.perf_counter()
-d = pipeline.WavefrontDriver(pipeline.EngineBackend(eng), origin=origin, root_width=width, start_level=first_level, final_level=last_level, cameras=eng.cameras)
-out = d.run(seeds)
+out, stats = pipeline.run_native(eng, seeds, origin=origin, root_width=width, start_level=first_level, final_level=last_level)   # C++ driver
 t_ours = time.perf_counter() - t1
-ours = dict(seconds=t_ours, seconds_scene_upload_and_seeding=t_setup, seconds_optimize=d.stats.seconds_optimize, seconds_accept=d.stats.seconds_accept,
-            optimize_calls=d.stats.optimized_calls, per_level={lv: int(n_ext) for lv, n_ext, _ in d.stats.per_level},
+t2 = time.perf_counter()
+d = pipeline.WavefrontDriver(pipeline.EngineBackend(eng), origin=origin, root_width=width, start_level=first_level, final_level=last_level, cameras=eng.cameras)
+out_py = d.run(seeds)
+t_py = time.perf_counter() - t2
+ours = dict(seconds=t_ours, seconds_numpy_driver=t_py, drivers_identical=bool(out.tobytes() == out_py.tobytes()),
+            seconds_scene_upload_and_seeding=t_setup, seconds_optimize=stats.seconds_optimize, seconds_accept=stats.seconds_accept,
+            optimize_calls=stats.optimized_calls, per_level={lv: int(n_ext) for lv, n_ext, _ in stats.per_level},
             **quality(out["center"][:, :3].astype(np.float64), out["normal"][:, 2]))
 print(json.dumps({"workload": f"8-view 1280x960 synthetic plane, {n_seeds} NVM points, tree levels {first_level}..{last_level} (root cube {width:.4f})",
                   "reference_cli": ref_res, "b200_wavefront_driver": ours,

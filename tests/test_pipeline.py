@@ -78,3 +78,22 @@ def test_pipeline_same_patch_set_on_engine_and_oracle():
     # the loop really grew the cloud: more patches than accepted seeds, and they hug the plane z = 0
     assert sum(e for _, e, _ in d_gpu.stats.per_level) > 0
     assert np.abs(got["center"][:, 2]).mean() < 0.15
+
+
+@pytest.mark.gpu
+def test_native_driver_equals_python_driver():
+    """hpmvs_pipeline_run (C++ behind the C ABI, the product's host path) against the numpy driver above on the same engine: the same
+    patch array, byte for byte, and the same per-level statistics - with the image-cell de-duplication on and the CLI's PATCH_FINAL_MINLEVEL."""
+    sc = hp.synth.plane_scene(n_views=6, width=640, height=480, focal=600.0, n_seeds=150, seed=8, tex_size=512, depth_noise=0.3)
+    eng = hp.Engine.from_synth(sc)
+    seeds, valid = hp.seed_patches(eng.options, eng.cameras, sc.points, sc.meas_offsets, sc.meas_cam)
+    seeds = np.ascontiguousarray(seeds[valid])
+    width0 = float(np.median(seeds["scale"])) * 2.2
+    for fml in (0, 8):
+        args = dict(origin=(-8.0, -8.0, -8.0), root_width=width0 * 64, start_level=6, final_level=8, final_min_level=fml)
+        d = pipeline.WavefrontDriver(pipeline.EngineBackend(eng), cameras=eng.cameras, **args)
+        want = d.run(seeds)
+        got, st = pipeline.run_native(eng, seeds, dedup_ref_pixel=True, **args)
+        assert st.per_level == d.stats.per_level and st.optimized_calls == d.stats.optimized_calls
+        assert len(got) == len(want) and len(got) > 100
+        assert got.tobytes() == want.tobytes()
