@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="plane8", choices=["plane8", "plane8x100k", "city100", "tiny"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="patches in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--inflight", type=int, default=2, help="steps in flight (each on its own stream): >1 lets the next step's CTAs start on SMs the previous step has drained")
     return ap.parse_args()
 
 
@@ -238,32 +239,37 @@ def main():
     seeds = np.ascontiguousarray(seeds[valid])
     n = len(seeds)
 
-    stream = torch.cuda.Stream()          # a real (non-legacy) stream: its handle is what the C ABI launches on
+    F = max(1, int(args.inflight))
+    streams = [torch.cuda.Stream() for _ in range(F)]     # real (non-legacy) streams: their handles are what the C ABI launches on
+    stream = streams[0]
     torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
     assert sptr != 0
     rec = torch.from_numpy(seeds.view(np.uint8).reshape(n, REC_BYTES))
-    h_in = torch.empty((n, REC_BYTES), dtype=torch.uint8).pin_memory()
-    h_in.copy_(rec)
-    h_out = torch.empty((n, REC_BYTES), dtype=torch.uint8).pin_memory()
+    h_ins, h_outs = [], []
+    for _ in range(F):
+        hi = torch.empty((n, REC_BYTES), dtype=torch.uint8).pin_memory(); hi.copy_(rec)
+        h_ins.append(hi); h_outs.append(torch.empty((n, REC_BYTES), dtype=torch.uint8).pin_memory())
+    h_in, h_out = h_ins[0], h_outs[0]
     d_in = h_in.to("cuda", non_blocking=False)
-    d_out = torch.empty_like(d_in)
+    d_outs = [torch.empty_like(d_in) for _ in range(F)]
+    d_out = d_outs[0]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    flush_src = torch.zeros_like(flush)
+
+    def flush_l2():
+        # a 256 MiB device-to-device copy (copy engine): evicts L2 without needing an SM, so it cannot be held up behind the
+        # persistent CTAs of a step that is still draining
+        flush.copy_(flush_src, non_blocking=True)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device():
-        eng.optimize_device(n, d_in.data_ptr(), d_out.data_ptr(), sptr)
-
-    def step_e2e():
-        eng.optimize_ptr(n, h_in.data_ptr(), h_out.data_ptr(), sptr)
-
     # ---- warm-up ---------------------------------------------------------------------------------------------
-    for _ in range(max(3, args.warmup)):
-        step_device()
+    for k in range(max(3, args.warmup)):
+        eng.optimize_device(n, d_in.data_ptr(), d_outs[k % F].data_ptr(), streams[k % F].cuda_stream)
     torch.cuda.synchronize()
     eng.counters(reset=True)
 
@@ -272,41 +278,52 @@ def main():
         sampler.start()
         time.sleep(0.3)
 
-    # ---- timed: K steps, kernel only, records resident in HBM, L2 flushed between steps ---------------------
+    # ---- timed: K steps, kernel only, records resident in HBM, L2 flushed before every step.  With --inflight F > 1 step k runs
+    # on stream k % F, so the CTAs of step k+1 start on the SMs that step k has already drained; the region is timed with one
+    # event pair: start after all streams are idle, end after every stream has finished (a join stream waits for all of them) ------
     barrier()
-    evs = []
+    join = torch.cuda.Stream()
+    ev_start = torch.cuda.Event(enable_timing=True); ev_end = torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.zero_()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        step_device()
-        e1.record(stream)
-        evs.append((e0, e1))
+    ev_start.record(join)
+    for st in streams:
+        st.wait_event(ev_start)
+    for k in range(args.steps):
+        st = streams[k % F]
+        with torch.cuda.stream(st):
+            flush_l2()
+        eng.optimize_device(n, d_in.data_ptr(), d_outs[k % F].data_ptr(), st.cuda_stream)
+    for st in streams:
+        join.wait_stream(st)
+    ev_end.record(join)
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    kernel_ms = [a.elapsed_time(b) for a, b in evs]
-    t_dev = sum(kernel_ms) / 1e3
+    t_dev = ev_start.elapsed_time(ev_end) / 1e3
     cnt = eng.counters(reset=True)
     ok_per_step = cnt.patches_ok / args.steps
     tex_per_step = cnt.textures / args.steps
     evals_per_step = cnt.evals / args.steps
     launches_timed = int(cnt.kernel_launches)
 
-    # ---- timed: e2e through the C ABI with pinned host buffers ----------------------------------------------
-    for _ in range(2):
-        step_e2e()
+    # ---- timed: e2e through the C ABI with pinned host buffers (H2D + kernel + D2H per step), same streams ------------------
+    for k in range(2):
+        eng.optimize_submit(n, h_ins[k % F].data_ptr(), h_outs[k % F].data_ptr(), streams[k % F].cuda_stream)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.zero_()
-        step_e2e()
+    for k in range(args.steps):
+        st = streams[k % F]
+        with torch.cuda.stream(st):
+            flush_l2()
+        eng.optimize_submit(n, h_ins[k % F].data_ptr(), h_outs[k % F].data_ptr(), st.cuda_stream)
     barrier()
     t_e2e = time.perf_counter() - t0
     # subtract nothing: the flush is a few hundred microseconds per step and stays inside (conservative)
     clocks = sampler.finish() if sampler else None
     out_np = h_out.numpy().view(hp.PATCH_DTYPE).reshape(n)
     ok_e2e = int((out_np["status"] == 0).sum())
+    for ho in h_outs[1:]:
+        assert np.array_equal(ho.numpy(), h_out.numpy()), "overlapping batches must return identical records"
+    torch.cuda.set_stream(stream)
 
     # ---- the stand-alone scoring kernel (K1 = PatchOptimizer::setINCCs for a batch: the gather + NCC part of the path without the
     # optimizer around it), device-resident records, timed with CUDA events; reported as `roofline_ncc` ------------------------------
@@ -320,7 +337,7 @@ def main():
     eng.counters(reset=True)
     ncc_evs = []
     for _ in range(max(3, args.steps // 2)):
-        flush.zero_()
+        flush_l2()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         eng.ncc_device(nb, d_big.data_ptr(), d_inc.data_ptr(), 0, False, sptr)
@@ -388,7 +405,8 @@ def main():
                 "warmup": max(3, args.warmup), "ms_per_step": 1e3 * t_dev_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 samples / f64 optimizer", "data": "synthetic",
                 "config": {"workload": desc, "patches_per_step_per_gpu": int(n), "optimized_per_step": ok_all,
-                           "evals_per_step": evals_all, "textures_per_step": tex_all, "l2": "flushed between steps (256 MiB write)",
+                           "evals_per_step": evals_all, "textures_per_step": tex_all, "l2": "flushed before every step (256 MiB device-to-device copy on the step's stream)",
+                           "steps_in_flight": F,
                            "parallelism": f"patch shards x{world}, scene replicated, no data-path collective",
                            "wall_s_timed_region": t_wall, "final_gather_dedup_ms": gather_ms,
                            "patches_gathered_kept": merged},
@@ -399,7 +417,7 @@ def main():
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": peak_src, "kernel": "hp::optimize_kernel",
                              "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": 1e3 * mean_launch_s,
-                             "note": "algorithmic gather bytes (588 B/texture, no reuse credit); the footprint is L1-resident so DRAM traffic is far lower - kernel is issue/latency bound, see DESIGN.md"},
+                             "note": "algorithmic gather bytes (588 B/texture, no reuse credit); launch_ms = timed region / launches (launches of consecutive steps overlap when steps_in_flight > 1); the footprint is L1-resident so DRAM traffic is far lower - kernel is issue/latency bound, see DESIGN.md"},
                 "roofline_ncc": {"bound": "hbm", "kernel": "hp::ncc_kernel (setINCCs for a batch: projection, 7x7 bilinear RGB gather, normalise, NCC)",
                                  "achieved": (TEX_BYTES * ncc_tex_per_launch + (REC_BYTES + 4 * hp.MAX_VIEWS) * nb) / ncc_launch_s / 1e9,
                                  "peak": peak, "unit": "GB/s",

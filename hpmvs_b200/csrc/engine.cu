@@ -47,6 +47,8 @@ inline void h_normalized3(const float* a, float* o) {
 
 }  // namespace
 
+enum { HP_RING = 4 };
+
 struct hpmvs_engine {
     int device = 0;
     int sm_count = 0;
@@ -71,6 +73,10 @@ struct hpmvs_engine {
     hpmvs_patch_t* d_out = nullptr;
     float* d_inccs = nullptr;
     size_t cap_patches = 0, cap_inccs = 0;
+    // hpmvs_optimize_batch_submit: a second staging set so that two host-buffer batches can be in flight
+    struct Stage { hpmvs_patch_t* d_in = nullptr; hpmvs_patch_t* d_out = nullptr; size_t cap = 0; double* d_start = nullptr;
+                   double* h_start = nullptr; size_t cap_start = 0; cudaEvent_t done = nullptr; } stage2[2];
+    unsigned long long submit_seq = 0;
     int start_mode = 0;              // hpmvs_engine_set_start_mode
     double* d_start = nullptr;       // host-evaluated start angles of the batch (start_mode 1)
     double* h_start = nullptr;       // pinned staging for them
@@ -78,7 +84,9 @@ struct hpmvs_engine {
     const double* next_start = nullptr;   // device array handed to the next launch (consumed by launch_optimize)
     unsigned char* d_stage = nullptr;
     size_t cap_stage = 0;
-    int* d_work = nullptr;
+    int* d_work = nullptr;           // HP_RING work counters: launches on different streams may be in flight together
+    cudaEvent_t slot_done[4] = {nullptr, nullptr, nullptr, nullptr};   // slot k is reused only after its previous launch finished
+    unsigned long long launch_seq = 0;
     unsigned long long* d_counters = nullptr;
     unsigned long long launches = 0;
     size_t smem_bytes = 0, smem_opt_bytes = 0;
@@ -87,9 +95,11 @@ struct hpmvs_engine {
     int variant = 0;
     int pvariant = 0;
     int parked_mode = -1;            // -1 auto, 0 never, 1 always (HPMVS_PARKED)
-    hp::BqSlot* d_pool_bq = nullptr;
-    hp::LaneCtx* d_pool_ctx = nullptr;
-    int pool_ctas = 0;
+    hp::BqSlot* d_pool_bq2[2] = {nullptr, nullptr};     // parked variant: two pool sets, so that two launches can overlap
+    hp::LaneCtx* d_pool_ctx2[2] = {nullptr, nullptr};
+    int pool_ctas2[2] = {0, 0};
+    cudaEvent_t pool_done[2] = {nullptr, nullptr};
+    unsigned long long parked_seq = 0;
     std::mutex mu;
 };
 
@@ -208,7 +218,8 @@ int hpmvs_engine_create(const hpmvs_options_t* opt, int device, hpmvs_engine_t**
     HP_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     HP_CUDA(cudaEventCreate(&e->ev0));
     HP_CUDA(cudaEventCreate(&e->ev1));
-    HP_CUDA(cudaMalloc(&e->d_work, sizeof(int)));
+    HP_CUDA(cudaMalloc(&e->d_work, HP_RING * sizeof(int)));
+    for (int i = 0; i < HP_RING; i++) HP_CUDA(cudaEventCreateWithFlags(&e->slot_done[i], cudaEventDisableTiming));
     HP_CUDA(cudaMalloc(&e->d_counters, 16 * sizeof(unsigned long long)));
     HP_CUDA(cudaMemset(e->d_counters, 0, 16 * sizeof(unsigned long long)));
     e->smem_bytes = sizeof(hp::NccWarp) * hp::WARPS_PER_BLOCK;             // ncc_kernel
@@ -250,11 +261,14 @@ void hpmvs_engine_destroy(hpmvs_engine_t* e) {
         for (auto* d : cam)
             if (d) cudaFree(d);
     cudaFree(e->d_accept);
-    cudaFree(e->d_pool_bq); cudaFree(e->d_pool_ctx);
+    for (int i = 0; i < 2; i++) if (e->pool_done[i]) cudaEventDestroy(e->pool_done[i]);
     cudaFree(e->d_cams); cudaFree(e->d_covis_off); cudaFree(e->d_covis_ids);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_inccs); cudaFree(e->d_stage);
     cudaFree(e->d_start); if (e->h_start) cudaFreeHost(e->h_start);
+    for (auto& st : e->stage2) { cudaFree(st.d_in); cudaFree(st.d_out); cudaFree(st.d_start); if (st.h_start) cudaFreeHost(st.h_start); if (st.done) cudaEventDestroy(st.done); }
     cudaFree(e->d_work); cudaFree(e->d_counters);
+    for (int i = 0; i < HP_RING; i++) if (e->slot_done[i]) cudaEventDestroy(e->slot_done[i]);
+    for (int i = 0; i < 2; i++) { cudaFree(e->d_pool_bq2[i]); cudaFree(e->d_pool_ctx2[i]); }
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
     cudaStreamDestroy(e->stream);
     delete e;
@@ -433,8 +447,14 @@ static int launch_optimize(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, hp
     if (rc) return rc;
     rc = sync_cameras(e);
     if (rc) return rc;
-    HP_CUDA(cudaMemsetAsync(e->d_work, 0, sizeof(int), s));
+    // launches on different streams overlap (a CTA of the next launch starts on an SM as soon as the previous launch's CTA
+    // there has drained its slots): every launch gets its own work counter from a small ring; a ring slot is reused only after
+    // the launch that used it last has completed
+    const int slot = (int)(e->launch_seq++ % HP_RING);
+    HP_CUDA(cudaStreamWaitEvent(s, e->slot_done[slot], 0));
+    HP_CUDA(cudaMemsetAsync(e->d_work + slot, 0, sizeof(int), s));
     hp::KParams K = make_params(e, d_in, d_out, n);
+    K.work_counter = e->d_work + slot;
     // persistent grid: one warp-specialised CTA per SM.  Each optimizer warp keeps `lanes` patches in flight;
     // small batches are spread over all SMs first (lanes < 32) so that no SM idles.
     const KernelVariant& V = g_variants[e->variant];
@@ -457,12 +477,15 @@ static int launch_optimize(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, hp
         const ParkedVariant& PV = g_pvariants[e->pvariant];
         const int g_parked_ow = PV.ow;
         grid = e->sm_count;
-        if (e->pool_ctas < grid) {
-            cudaFree(e->d_pool_bq); cudaFree(e->d_pool_ctx);
-            e->d_pool_bq = nullptr; e->d_pool_ctx = nullptr; e->pool_ctas = 0;
-            HP_CUDA(cudaMalloc(&e->d_pool_bq, sizeof(hp::BqSlot) * (size_t)grid * hp::VMAX));
-            HP_CUDA(cudaMalloc(&e->d_pool_ctx, sizeof(hp::LaneCtx) * (size_t)grid * hp::VMAX));
-            e->pool_ctas = grid;
+        const int ps = (int)(e->parked_seq++ % 2);
+        if (!e->pool_done[ps]) HP_CUDA(cudaEventCreateWithFlags(&e->pool_done[ps], cudaEventDisableTiming));
+        HP_CUDA(cudaStreamWaitEvent(s, e->pool_done[ps], 0));
+        if (e->pool_ctas2[ps] < grid) {
+            cudaFree(e->d_pool_bq2[ps]); cudaFree(e->d_pool_ctx2[ps]);
+            e->d_pool_bq2[ps] = nullptr; e->d_pool_ctx2[ps] = nullptr; e->pool_ctas2[ps] = 0;
+            HP_CUDA(cudaMalloc(&e->d_pool_bq2[ps], sizeof(hp::BqSlot) * (size_t)grid * hp::VMAX));
+            HP_CUDA(cudaMalloc(&e->d_pool_ctx2[ps], sizeof(hp::LaneCtx) * (size_t)grid * hp::VMAX));
+            e->pool_ctas2[ps] = grid;
         }
         int v = (n + grid - 1) / grid;                          // virtual slots per CTA: all patches in flight if they fit
         v = (v + g_parked_ow - 1) / g_parked_ow * g_parked_ow;
@@ -470,11 +493,13 @@ static int launch_optimize(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, hp
         if (v < g_parked_ow) v = g_parked_ow;
         if (const char* vs = getenv("HPMVS_VSLOTS")) { v = atoi(vs) / g_parked_ow * g_parked_ow; if (v < g_parked_ow) v = g_parked_ow; if (v > hp::VMAX) v = hp::VMAX; }
         K.vslots = v;
-        K.pool_bq = e->d_pool_bq;
-        K.pool_ctx = e->d_pool_ctx;
+        K.pool_bq = e->d_pool_bq2[ps];
+        K.pool_ctx = e->d_pool_ctx2[ps];
         PV.fn<<<grid, (PV.ow + PV.sw) * 32, PV.smem, s>>>(K);
+        HP_CUDA(cudaEventRecord(e->pool_done[ps], s));
     }
     HP_CUDA(cudaEventRecord(e->ev1, s));
+    HP_CUDA(cudaEventRecord(e->slot_done[slot], s));
     e->launches++;
     HP_CUDA(cudaGetLastError());
     return 0;
@@ -532,6 +557,57 @@ int hpmvs_optimize_batch(hpmvs_engine_t* e, int n, const hpmvs_patch_t* in, hpmv
     HP_CUDA(cudaMemcpyAsync(out, e->d_out, sizeof(hpmvs_patch_t) * n, cudaMemcpyDeviceToHost, s));
     HP_CUDA(cudaStreamSynchronize(s));
     cudaEventElapsedTime(&e->last_kernel_ms, e->ev0, e->ev1);
+    return 0;
+}
+
+// Asynchronous form of hpmvs_optimize_batch: H2D, kernel and D2H are only ENQUEUED on `stream` (which must not be NULL); the
+// call returns at once and the caller synchronises its stream.  Two staging sets alternate, so two batches submitted on two
+// streams overlap: the next batch's CTAs start on the SMs the previous batch has already drained.
+int hpmvs_optimize_batch_submit(hpmvs_engine_t* e, int n, const hpmvs_patch_t* in, hpmvs_patch_t* out, void* stream) {
+    if (!e || !stream || n < 0 || (n > 0 && (!in || !out))) return HPMVS_E_ARG;
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(e->mu);
+    HP_CUDA(cudaSetDevice(e->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = check_ready(e);
+    if (rc) return rc;
+    for (int i = 0; i < n; i++) {
+        const int k = in[i].nimages < HPMVS_MAX_VIEWS ? in[i].nimages : HPMVS_MAX_VIEWS;
+        for (int j = 0; j < k; j++)
+            if (in[i].images[j] < 0 || in[i].images[j] >= e->ncams) return HPMVS_E_ARG;
+    }
+    hpmvs_engine::Stage& st = e->stage2[e->submit_seq++ % 2];
+    if (!st.done) HP_CUDA(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+    if ((size_t)n > st.cap) {
+        HP_CUDA(cudaEventSynchronize(st.done));
+        cudaFree(st.d_in); cudaFree(st.d_out); st.d_in = st.d_out = nullptr; st.cap = 0;
+        const size_t cap = (size_t)n + (size_t)n / 4 + 1024;
+        HP_CUDA(cudaMalloc(&st.d_in, cap * sizeof(hpmvs_patch_t)));
+        HP_CUDA(cudaMalloc(&st.d_out, cap * sizeof(hpmvs_patch_t)));
+        st.cap = cap;
+    }
+    if (e->start_mode == 1) {
+        HP_CUDA(cudaEventSynchronize(st.done));          // the pinned angle buffer of this set is free again
+        if ((size_t)n > st.cap_start) {
+            cudaFree(st.d_start); if (st.h_start) cudaFreeHost(st.h_start);
+            st.d_start = nullptr; st.h_start = nullptr; st.cap_start = 0;
+            const size_t cap = (size_t)n + (size_t)n / 4 + 1024;
+            HP_CUDA(cudaMalloc(&st.d_start, cap * 2 * sizeof(double)));
+            HP_CUDA(cudaMallocHost(&st.h_start, cap * 2 * sizeof(double)));
+            st.cap_start = cap;
+        }
+        host_start_parameters(e, n, in, st.h_start);
+    }
+    HP_CUDA(cudaStreamWaitEvent(s, st.done, 0));         // the previous batch that used this staging set has left it
+    HP_CUDA(cudaMemcpyAsync(st.d_in, in, sizeof(hpmvs_patch_t) * n, cudaMemcpyHostToDevice, s));
+    if (e->start_mode == 1) {
+        HP_CUDA(cudaMemcpyAsync(st.d_start, st.h_start, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, s));
+        e->next_start = st.d_start;
+    }
+    rc = launch_optimize(e, n, st.d_in, st.d_out, s);
+    if (rc) return rc;
+    HP_CUDA(cudaMemcpyAsync(out, st.d_out, sizeof(hpmvs_patch_t) * n, cudaMemcpyDeviceToHost, s));
+    HP_CUDA(cudaEventRecord(st.done, s));
     return 0;
 }
 

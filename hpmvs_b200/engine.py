@@ -72,6 +72,7 @@ def _lib():
         L.hpmvs_ncc_batch.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, fp, vp]
         L.hpmvs_ncc_batch_device.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, vp]
         L.hpmvs_engine_set_start_mode.argtypes = [vp, C.c_int]
+        L.hpmvs_optimize_batch_submit.argtypes = [vp, C.c_int, vp, vp, vp]
         L.hpmvs_engine_counters.argtypes = [vp, C.POINTER(Counters), C.c_int]
         L.hpmvs_engine_stream.argtypes = [vp]; L.hpmvs_engine_stream.restype = vp
         L.hpmvs_engine_last_kernel_ms.argtypes = [vp]; L.hpmvs_engine_last_kernel_ms.restype = C.c_float
@@ -223,6 +224,10 @@ class Engine:
     def optimize_ptr(self, n: int, in_ptr: int, out_ptr: int, stream: int = 0) -> None:
         """Same, on raw host pointers (e.g. pinned torch tensors)."""
         _check(_lib().hpmvs_optimize_batch(self._h, n, in_ptr, out_ptr, stream or None))
+
+    def optimize_submit(self, n: int, in_ptr: int, out_ptr: int, stream: int) -> None:
+        """Asynchronous host-buffer call (pinned pointers): enqueues H2D + kernel + D2H on `stream` and returns."""
+        _check(_lib().hpmvs_optimize_batch_submit(self._h, n, in_ptr, out_ptr, stream))
 
     def optimize_device(self, n: int, d_in: int, d_out: int, stream: int = 0) -> None:
         """Device-resident records, asynchronous on `stream` (0 = the engine's stream)."""

@@ -71,6 +71,31 @@ def test_setinccs_device_resident_call(plane):
     assert eng.last_kernel_ms() > 0.0
 
 
+def test_overlapping_submits_return_the_same_records(plane):
+    # hpmvs_optimize_batch_submit: two batches in flight on two streams (the second starts on SMs the first has drained), in both start modes
+    import torch
+    sc, orc, seeds, eng = plane
+    pe = to_engine(seeds)
+    want = eng.optimize(pe)
+    n = len(pe)
+    raw = torch.from_numpy(pe.view(np.uint8).reshape(n, -1).copy())
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for mode in (False, True):
+        eng.set_start_mode(mode)
+        try:
+            ref_out = eng.optimize(pe)
+            h_in = [raw.clone().pin_memory() for _ in range(4)]
+            h_out = [torch.zeros_like(raw).pin_memory() for _ in range(4)]
+            for k in range(4):
+                eng.optimize_submit(n, h_in[k].data_ptr(), h_out[k].data_ptr(), streams[k % 2].cuda_stream)
+            torch.cuda.synchronize()
+            for k in range(4):
+                assert np.array_equal(h_out[k].numpy().view(hp.PATCH_DTYPE).reshape(n), ref_out), (mode, k)
+        finally:
+            eng.set_start_mode(False)
+    assert np.array_equal(want, eng.optimize(pe))
+
+
 def test_optimize_bit_exact_with_correctly_rounded_asinf(plane):
     sc, orc, seeds, eng = plane
     oracle.set_cr_asinf(True)
@@ -189,7 +214,8 @@ def test_config1_full_size_against_the_reference_path():
     assert len(seeds) == 10000 and ok.sum() > 9000
     assert np.array_equal(got["status"] == 0, ok)
     assert np.array_equal(got["nimages"][ok], want["nimages"][ok])
-    assert np.array_equal(got["images"][ok], want["images"][ok][:, :hp.MAX_VIEWS])
+    for a, b, k in zip(got["images"][ok], want["images"][ok], want["nimages"][ok]):
+        assert np.array_equal(a[:k], b[:k])                       # entries past nimages are unspecified
     bit = np.array([np.array_equal(got[f][ok][i], want[f][ok][i]) for f in ("center", "normal", "color") for i in range(int(ok.sum()))]).reshape(3, -1).all(0)
     assert bit.mean() >= 0.999, bit.mean()
     dc = np.linalg.norm(got["center"][ok][:, :3] - want["center"][ok][:, :3], axis=1) / got["scale"][ok]
