@@ -9,6 +9,8 @@
 #include <strings.h>
 
 #include <algorithm>
+#include <cmath>
+#include <complex>
 #include <fstream>
 #include <sstream>
 #include <string>
@@ -134,6 +136,78 @@ int hpmvs_ppm_read(const char* path, int* width, int* height, uint8_t* rgb) {
     }
     fclose(fh);
     return rc;
+}
+
+// Image::undistort (src/hpmvs/Image.cpp:68-149): VisualSFM's one-parameter radial model undone on the level-0 image.
+// For every target pixel the distorted source position is found in closed form (Cardano, double / complex<double> exactly as
+// the reference writes it), sampled with CImg's _linear_atXY (thirdLibs/cimg/CImg.h:12218-12235, f32) when it lies strictly
+// inside the 1-pixel border, and the f32 result is truncated to u8 when the float image is assigned back (Image.cpp:143-144).
+// Pixels whose source falls outside stay 0 (the reference leaves its freshly allocated float buffer untouched there, Q13).
+// Host code on purpose: pow / sqrt / complex pow come from the same libm the reference would use.
+int hpmvs_undistort_rgb(const uint8_t* rgb, int width, int height, double f_in, double k1_in, uint8_t* out, uint8_t* written) {
+    if (!rgb || !out || width <= 0 || height <= 0) return HPMVS_E_ARG;
+    const float f_ = (float)f_in, k1_ = (float)k1_in;           // Image::init stores them as float (Image.cpp:36-37, Image.h:78)
+    const size_t npx = (size_t)width * height;
+    if (k1_ == 0) { memcpy(out, rgb, 3 * npx); if (written) memset(written, 1, npx); return 0; }   // Image::load only calls undistort() when k1_ != 0 (Image.cpp:51)
+    memset(out, 0, 3 * npx);
+    if (written) memset(written, 0, npx);
+    auto at = [&](unsigned x, unsigned y, int c) -> float { return (float)rgb[3 * ((size_t)y * width + x) + c]; };
+    for (int ix = 0; ix < width; ix++) {
+        for (int iy = 0; iy < height; iy++) {
+            float y = (float)(iy - height / 2.0);
+            float x = (float)(ix - width / 2.0);
+            x /= f_;
+            y /= f_;
+            if (y == 0) y = 1e-3;
+            float mx, my;
+            {
+                const double t2 = y * y;
+                const double t3 = t2 * t2 * t2;
+                const double t4 = x * x;
+                const double t7 = k1_ * (t2 + t4);
+                if (k1_ > 0) {
+                    const double t8 = 1.0 / t7;
+                    const double t10 = t3 / (t7 * t7);
+                    const double t14 = sqrt(t10 * (0.25 + t8 / 27.0));
+                    const double t15 = t2 * t8 * y * 0.5;
+                    const double t17 = pow(t14 + t15, 1.0 / 3.0);
+                    const double t18 = t17 - t2 * t8 / (t17 * 3.0);
+                    mx = t18 * x / y;
+                    my = t18;
+                } else {
+                    const double t9 = t3 / (t7 * t7 * 4.0);
+                    const double t11 = t3 / (t7 * t7 * t7 * 27.0);
+                    const std::complex<double> t12 = t9 + t11;
+                    const std::complex<double> t13 = sqrt(t12);
+                    const double t14 = t2 / t7;
+                    const double t15 = t14 * y * 0.5;
+                    const std::complex<double> t16 = t13 + t15;
+                    const std::complex<double> t17 = pow(t16, 1.0 / 3.0);
+                    const std::complex<double> t18 = (t17 + t14 / (t17 * 3.0)) * std::complex<double>(0.0, sqrt(3.0));
+                    const std::complex<double> t19 = -0.5 * (t17 + t18) + t14 / (t17 * 6.0);
+                    mx = t19.real() * x / y;
+                    my = t19.real();
+                }
+            }
+            x = mx * (float)f_ + width / 2.0f;
+            y = my * (float)f_ + height / 2.0f;
+            if (x > 1 && x < width - 1 && y > 1 && y < height - 1) {
+                // CImg<unsigned char>::_linear_atXY(x, y, 0, c)
+                const unsigned W = (unsigned)width, H = (unsigned)height;
+                const float nfx = x < 0 ? 0 : (x > W - 1 ? W - 1 : x), nfy = y < 0 ? 0 : (y > H - 1 ? H - 1 : y);
+                const unsigned px = (unsigned)nfx, py = (unsigned)nfy;
+                const float dx = nfx - px, dy = nfy - py;
+                const unsigned nx = dx > 0 ? px + 1 : px, ny = dy > 0 ? py + 1 : py;
+                for (int c = 0; c < 3; c++) {
+                    const float Icc = at(px, py, c), Inc = at(nx, py, c), Icn = at(px, ny, c), Inn = at(nx, ny, c);
+                    const float v = Icc + dx * (Inc - Icc + dy * (Icc + Inn - Icn - Inc)) + dy * (Icn - Icc);
+                    out[3 * ((size_t)iy * width + ix) + c] = (uint8_t)v;
+                }
+                if (written) written[(size_t)iy * width + ix] = 1;
+            }
+        }
+    }
+    return 0;
 }
 
 int hpmvs_ply_write_ext(const char* path, int n, const hpmvs_patch_t* p, int binary, int normal, int scale, int visibility) {

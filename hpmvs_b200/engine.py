@@ -202,6 +202,9 @@ class Engine:
         cams = [camera_from_nvm(c.f, c.q, c.c, img.shape[1], img.shape[0], ml) for c, img in zip(scene.cameras, scene.images)]
         e.set_cameras(cams)
         for i, img in enumerate(scene.images):
+            if getattr(scene.cameras[i], "r", 0.0) != 0.0:          # Image::load undistorts level 0 first (Image.cpp:51-53)
+                from . import io as _io
+                img = _io.undistort(img, scene.cameras[i].f, scene.cameras[i].r)
             e.upload_image(i, 0, img)
             e.build_pyramid(i)
         e.set_covis(extract_covis(len(cams), scene.meas_offsets, scene.meas_cam, compat_covis))

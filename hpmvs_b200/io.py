@@ -68,6 +68,18 @@ def read_nvm(path: str, fix_path: bool = True, load_images: bool = True) -> Synt
     return SynthScene(os.path.basename(path), cams, images, xyz, offs, mc[:nm])
 
 
+def undistort(rgb: np.ndarray, f: float, r: float, return_mask: bool = False):
+    """Image::undistort (Image.cpp:68-149) on an [h, w, 3] u8 image; r == 0 returns a copy.  return_mask: also the [h, w] bool mask of
+    the pixels that were written (the others are 0 here and uninitialised memory in the reference)."""
+    img = np.ascontiguousarray(rgb, np.uint8)
+    out = np.empty_like(img)
+    mask = np.zeros(img.shape[:2], np.uint8)
+    L = _lib()
+    L.hpmvs_undistort_rgb.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+    _check(L.hpmvs_undistort_rgb(img.ctypes.data, img.shape[1], img.shape[0], float(f), float(r), out.ctypes.data, mask.ctypes.data))
+    return (out, mask.astype(bool)) if return_mask else out
+
+
 def write_ext_ply(path: str, patches: np.ndarray, binary: bool = False, normal: bool = True, scale: bool = True,
                   visibility: bool = True) -> None:
     """DynOctTree::toExtPly for a flat list of patch records (doctree.h:525-622)."""

@@ -245,6 +245,12 @@ int  hpmvs_nvm_camera(const hpmvs_nvm_t *m, int i, char *filename, int cap, doub
 /* any output pointer may be NULL; offsets has num_points+1 entries (CSR over the measurement arrays) */
 int  hpmvs_nvm_points(const hpmvs_nvm_t *m, double *xyz, double *rgb, int32_t *offsets, int32_t *meas_cam,
                       int32_t *meas_feat, double *meas_xy);
+/* Replaces Image::undistort (src/hpmvs/Image.cpp:68-149): undoes VisualSFM's radial distortion `r` (NVM camera line, NVMReader.cpp:70)
+ * on an interleaved u8 RGB level-0 image with focal length f, before the pyramid is built; r == 0 copies.  Host function (same libm
+ * as the reference for its pow / complex pow), bit-exact against the reference build incl. the f32 -> u8 truncation.  Target pixels
+ * whose source falls outside the image are left 0 (the reference leaves them UNINITIALISED, Image.cpp:79); `written` (width*height
+ * bytes, may be NULL) marks the pixels that were set. */
+int  hpmvs_undistort_rgb(const uint8_t *rgb, int width, int height, double f, double r, uint8_t *out, uint8_t *written);
 /* Level-0 image reader (binary PPM "P6", maxval 255); call with rgb == NULL to get the size first. */
 int  hpmvs_ppm_read(const char *path, int *width, int *height, uint8_t *rgb);
 /* Replaces DynOctTree::toExtPly (include/hpmvs/doctree.h:525-622): vertex element {x y z [nx ny nz] red green blue

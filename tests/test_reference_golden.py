@@ -159,3 +159,28 @@ def test_live_reference_primitives():
         p = img.astype(np.float32)
         want = (p[ly, lx] * f00 + p[ly + 1, lx] * f01) + (p[ly, lx + 1] * f10 + p[ly + 1, lx + 1] * f11)
         assert np.array_equal(rs.get_color(0, x, y, 1), want.astype(np.float32))
+
+
+@needs_ref
+@pytest.mark.parametrize("r", [0.08, -0.06])
+def test_live_reference_radial_undistortion(r):
+    # next row f-1: Image::undistort (Image.cpp:68-149) for both signs of VisualSFM's radial parameter: hpmvs_undistort_rgb against
+    # the reference's loader, bit for bit on every pixel the reference WRITES (it leaves the others uninitialised, Image.cpp:79 - Q13);
+    # the pyramid on top is checked on the reference's own level 0, garbage included
+    from hpmvs_b200 import io as hio
+    sc = hp.synth.plane_scene(n_views=3, width=321, height=243, focal=300.0, n_seeds=30, seed=4, tex_size=128)
+    for cam in sc.cameras:
+        cam.r = r
+    rs = ref.RefScene.from_synth(sc)
+    orc = oracle.OracleScene()
+    for i, (cam, img) in enumerate(zip(sc.cameras, sc.images)):
+        und, written = hio.undistort(img, cam.f, cam.r, return_mask=True)
+        ref0 = rs.image(i, 0)
+        assert written.mean() > 0.9 and not np.array_equal(und, img)
+        assert np.array_equal(und[written], ref0[written])
+        orc.add_camera(cam.f, cam.q, cam.c, ref0)
+    for i in range(rs.n_cameras):
+        for lvl in range(1, 6):
+            assert np.array_equal(orc.image(i, lvl), rs.image(i, lvl)), (i, lvl)
+    # r == 0 is the identity (Image::load does not call undistort then, Image.cpp:51)
+    assert np.array_equal(hio.undistort(sc.images[0], 300.0, 0.0), sc.images[0])
