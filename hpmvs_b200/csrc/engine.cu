@@ -483,7 +483,7 @@ static int launch_optimize(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, hp
         if (e->pool_ctas2[ps] < grid) {
             cudaFree(e->d_pool_bq2[ps]); cudaFree(e->d_pool_ctx2[ps]);
             e->d_pool_bq2[ps] = nullptr; e->d_pool_ctx2[ps] = nullptr; e->pool_ctas2[ps] = 0;
-            HP_CUDA(cudaMalloc(&e->d_pool_bq2[ps], sizeof(hp::BqSlot) * (size_t)grid * hp::VMAX));
+            HP_CUDA(cudaMalloc(&e->d_pool_bq2[ps], sizeof(hp::BqSlotP) * (size_t)grid * hp::VMAX));
             HP_CUDA(cudaMalloc(&e->d_pool_ctx2[ps], sizeof(hp::LaneCtx) * (size_t)grid * hp::VMAX));
             e->pool_ctas2[ps] = grid;
         }

@@ -1075,15 +1075,59 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
 constexpr int VMAX = 256;
 constexpr int MIN_BATCH = 12;            // lanes worth starting an optimizer round for while objectives are still pending
 
+// Parked variant: the staging slots are filled and drained by the bulk-async copy engine (cp.async.bulk, SASS UBLKCP), which needs
+// 16-byte aligned addresses and sizes: the slot is the bare State (1616 B = 16 * 101).  Its stride is an even number of 8-byte words,
+// so lane-parallel FP64 accesses take 2-way bank conflicts here (the resident variant keeps the conflict-free odd stride) - the
+// optimizer warps are latency bound, the copies were 13 % of their time.
+#ifndef HP_PARKED_TMA
+#define HP_PARKED_TMA 1
+#endif
+#if HP_PARKED_TMA
+struct __align__(16) BqSlotP { bq3::State s; };
+static_assert(sizeof(BqSlotP) % 16 == 0 && sizeof(LaneCtx) % 16 == 0, "bulk copies move multiples of 16 bytes");
+#else
+typedef BqSlot BqSlotP;
+#endif
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+// global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> global, tracked by the issuing thread's bulk group
+__device__ __forceinline__ void bulk_s2g(void* gmem, const void* smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem), "r"(smem_u32(smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_all() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 template <int OPT_WARPS, int SAMPLER_WARPS, int LPW>
 struct __align__(16) CtaSharedP {
-    BqSlot stage_bq[OPT_WARPS * LPW];
+    BqSlotP stage_bq[OPT_WARPS * LPW];
     LaneCtx stage_ctx[OPT_WARPS * LPW];
     int claim[OPT_WARPS][32];
     double fval[VMAX];
     int sstate[VMAX];
     QueueShared Q;
     struct Samp { Scratch S; LaneCtx P; } samp[SAMPLER_WARPS];
+    unsigned long long mbar[OPT_WARPS];          // one transaction barrier per optimizer warp (stage-in of a round)
 };
 
 // warp-cooperative copies between the pool (global, read/written around L1) and shared memory, 16 bytes per lane
@@ -1115,12 +1159,18 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int V = K.vslots;                       // multiple of OPT_WARPS
-    BqSlot* pool_bq = K.pool_bq + (size_t)blockIdx.x * VMAX;
+    BqSlotP* pool_bq = reinterpret_cast<BqSlotP*>(K.pool_bq) + (size_t)blockIdx.x * VMAX;
     LaneCtx* pool_ctx = K.pool_ctx + (size_t)blockIdx.x * VMAX;
 
     for (int i = threadIdx.x; i < QCAP; i += blockDim.x) C.Q.queue[i] = 0;
     for (int i = threadIdx.x; i < VMAX; i += blockDim.x) C.sstate[i] = ST_DEAD;
-    if (threadIdx.x == 0) { C.Q.q_head = 0; C.Q.q_tail = 0; C.Q.opt_alive = OPT_WARPS; }
+    if (threadIdx.x == 0) {
+        C.Q.q_head = 0; C.Q.q_tail = 0; C.Q.opt_alive = OPT_WARPS;
+#if HP_PARKED_TMA
+        for (int i = 0; i < OPT_WARPS; i++) mbar_init(&C.mbar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+    }
     __syncthreads();
 
     if (warp < OPT_WARPS) {
@@ -1131,6 +1181,8 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
         LaneCtx& mine = C.stage_ctx[warp * LPW + (lane < LPW ? lane : 0)];
         bq3::State& bq = C.stage_bq[warp * LPW + (lane < LPW ? lane : 0)].s;
         int tries = 0;
+        unsigned mbar_phase = 0;
+        (void)mbar_phase;
         long long t_wait = 0, t_adv = 0, t_copy = 0, n_rounds = 0, n_lanes = 0;
         long long tw0 = HP_CLOCK();
         for (;;) {
@@ -1159,11 +1211,31 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
             const long long tc0 = HP_CLOCK();
             t_wait += tc0 - tw0; n_rounds++; n_lanes += count;
             // ---- stage in: context always, optimizer state unless the patch is new -------------------------------
+#if HP_PARKED_TMA
+            {
+                // lane j fetches slot j: two bulk-async copies (context, and the optimizer state unless the patch is new) that complete
+                // on the warp's transaction barrier; one wait for the whole round instead of one L2 round trip per slot
+                const int ej = (lane < count) ? C.claim[warp][lane] : 0;
+                const unsigned mybytes = (lane < count) ? (unsigned)sizeof(LaneCtx) + ((ej >> 16) ? 0u : (unsigned)sizeof(BqSlotP)) : 0u;
+                const unsigned total = __reduce_add_sync(FULL, mybytes);
+                fence_proxy_async();      // the pools were last written through the generic proxy (samplers) or by our own bulk stores
+                if (lane == 0) mbar_expect_tx(&C.mbar[warp], total);
+                __syncwarp();
+                if (lane < count) {
+                    const int sl = ej & 0xffff;
+                    bulk_g2s(&C.stage_ctx[warp * LPW + lane], &pool_ctx[sl], (unsigned)sizeof(LaneCtx), &C.mbar[warp]);
+                    if (!(ej >> 16)) bulk_g2s(&C.stage_bq[warp * LPW + lane], &pool_bq[sl], (unsigned)sizeof(BqSlotP), &C.mbar[warp]);
+                }
+                mbar_wait(&C.mbar[warp], mbar_phase);
+                mbar_phase ^= 1u;
+            }
+#else
             for (int j = 0; j < count; j++) {
                 const int e = C.claim[warp][j], slot = e & 0xffff;
                 copy_in<(int)sizeof(LaneCtx)>(&C.stage_ctx[warp * LPW + j], &pool_ctx[slot], lane);
                 if (!(e >> 16)) copy_in<BQ_COPY_BYTES>(&C.stage_bq[warp * LPW + j], &pool_bq[slot], lane);
             }
+#endif
             __syncwarp();
             const long long ta0 = HP_CLOCK();
             t_copy += ta0 - tc0;
@@ -1205,11 +1277,23 @@ __global__ void __launch_bounds__((OPT_WARPS + SAMPLER_WARPS) * 32, 1) optimize_
             const long long to0 = HP_CLOCK();
             t_adv += to0 - ta0;
             // ---- stage out and publish ------------------------------------------------------------------------------
+#if HP_PARKED_TMA
+            // lane j wrote slot j's state and context (generic proxy); make that visible to the async proxy, then drain both with bulk
+            // stores and wait for their completion before the slot is published
+            fence_proxy_async();
+            if (lane < count) {
+                bulk_s2g(&pool_ctx[slot], &C.stage_ctx[warp * LPW + lane], (unsigned)sizeof(LaneCtx));
+                bulk_s2g(&pool_bq[slot], &C.stage_bq[warp * LPW + lane], (unsigned)sizeof(BqSlotP));
+            }
+            bulk_commit_wait_all();
+            fence_proxy_async();
+#else
             for (int j = 0; j < count; j++) {
                 const int sl = C.claim[warp][j] & 0xffff;
                 copy_out<(int)sizeof(LaneCtx)>(&pool_ctx[sl], &C.stage_ctx[warp * LPW + j], lane);
                 copy_out<BQ_COPY_BYTES>(&pool_bq[sl], &C.stage_bq[warp * LPW + j], lane);
             }
+#endif
             __threadfence();
             __syncwarp();
             if (lane < count) {
