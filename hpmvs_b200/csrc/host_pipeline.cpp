@@ -220,4 +220,37 @@ int hpmvs_pipeline_run(hpmvs_engine_t* e, const hpmvs_pipeline_params_t* params,
 
 void hpmvs_free(void* p) { std::free(p); }
 
+// Border de-duplication after the final multi-GPU gather: patches of DIFFERENT ranks that fall into the same cubic cell of edge `cell`
+// are reduced to the best-supported one - most views first (CellProcessor::filter, src/hpmvs/CellProcessor.cpp:43-82), then the lower
+// final score, then the lower rank; patches of the winner's own rank in that cell all stay (merging inside a shard is the scheduler's
+// job).  keep[] receives the surviving indices in ascending order; returns their number.
+int hpmvs_dedup_border(int n, const hpmvs_patch_t* rec, const int32_t* owner, double cell, int32_t* keep) {
+    if (n < 0 || (n > 0 && (!rec || !owner || !keep)) || !(cell > 0.0)) return HPMVS_E_ARG;
+    struct Best { int idx; };
+    struct Key { int64_t k[3]; bool operator==(const Key& o) const { return k[0] == o.k[0] && k[1] == o.k[1] && k[2] == o.k[2]; } };
+    struct KeyHash { size_t operator()(const Key& a) const { return (size_t)(a.k[0] * 73856093ll ^ a.k[1] * 19349663ll ^ a.k[2] * 83492791ll); } };
+    std::unordered_map<Key, int, KeyHash> best;
+    std::vector<Key> keys((size_t)n);
+    auto better = [&](int a, int b) {     // a beats b
+        if (rec[a].nimages != rec[b].nimages) return rec[a].nimages > rec[b].nimages;
+        if (rec[a].score != rec[b].score) return rec[a].score < rec[b].score;
+        if (owner[a] != owner[b]) return owner[a] < owner[b];
+        return a < b;
+    };
+    for (int i = 0; i < n; i++) {
+        if (rec[i].status != HPMVS_OK) continue;
+        for (int a = 0; a < 3; a++) keys[i].k[a] = (int64_t)std::floor((double)rec[i].center[a] / cell);
+        auto it = best.find(keys[i]);
+        if (it == best.end()) best[keys[i]] = i;
+        else if (better(i, it->second)) it->second = i;
+    }
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        if (rec[i].status != HPMVS_OK) continue;
+        const int w = best[keys[i]];
+        if (i == w || owner[i] == owner[w]) keep[m++] = i;
+    }
+    return m;
+}
+
 }  // extern "C"

@@ -45,6 +45,19 @@ def gather_patches(records: np.ndarray, device: Optional[torch.device] = None) -
 
 
 def dedup_border(records: np.ndarray, owner: np.ndarray, cell: float) -> np.ndarray:
+    """hpmvs_dedup_border (host C++ behind the C ABI, hpmvs_b200/csrc/host_pipeline.cpp); dedup_border_numpy below is its twin."""
+    import ctypes as C
+    from . import engine as E
+    L = E._lib()
+    rec = np.ascontiguousarray(records); own = np.ascontiguousarray(owner, np.int32)
+    keep = np.zeros(max(len(rec), 1), np.int32)
+    L.hpmvs_dedup_border.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    m = L.hpmvs_dedup_border(len(rec), rec.ctypes.data, own.ctypes.data, float(cell), keep.ctypes.data)
+    E._check(m)
+    return keep[:m].astype(np.int64)
+
+
+def dedup_border_numpy(records: np.ndarray, owner: np.ndarray, cell: float) -> np.ndarray:
     """Keep one patch per cubic cell of edge `cell` when ranks disagree: most views first (CellProcessor::filter),
     then the lower final score, then the lower rank.  Patches of a single rank are never merged (that is the
     host scheduler's job inside a sub-tree).  Returns the indices kept, ascending."""

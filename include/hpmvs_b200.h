@@ -205,6 +205,11 @@ typedef struct hpmvs_pipeline_stats {
 int  hpmvs_pipeline_run(hpmvs_engine_t *e, const hpmvs_pipeline_params_t *params, int nseeds, const hpmvs_patch_t *seeds,
                         hpmvs_patch_t **out, int *nout, hpmvs_pipeline_stats_t *stats);
 void hpmvs_free(void *p);
+/* Border de-duplication after the final multi-GPU gather of the patch records (host C++; the gather itself is an NCCL all_gather,
+ * hpmvs_b200/gather.py): patches of different ranks (owner[i]) in the same cubic cell of edge `cell` are reduced to the best-supported
+ * one (most views, CellProcessor::filter, CellProcessor.cpp:43-82; then lower score, then lower rank); keep[] receives the surviving
+ * indices in ascending order (capacity n), the return value is their number. */
+int  hpmvs_dedup_border(int n, const hpmvs_patch_t *records, const int32_t *owner, double cell, int32_t *keep);
 
 /* ---- host-side scene surface (plain C++ on the host, no GPU needed): what feeds the engine ---- */
 

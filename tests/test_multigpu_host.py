@@ -57,6 +57,18 @@ def test_gather_and_dedup_world2():
     assert len(k0) == 15
 
 
+def test_dedup_native_equals_numpy_twin():
+    rng = np.random.default_rng(5)
+    for trial in range(5):
+        parts = [_make(int(rng.integers(0, 400)), r, rng) for r in range(4)]
+        allr = np.concatenate(parts)
+        owner = np.concatenate([np.full(len(p), r, np.int32) for r, p in enumerate(parts)])
+        allr["status"][rng.random(len(allr)) < 0.1] = 2
+        allr["nimages"][rng.random(len(allr)) < 0.5] = 5           # ties on the view count -> score, then rank decide
+        cell = [0.5, 0.2, 0.05, 1.5, 0.01][trial]
+        assert gather.dedup_border(allr, owner, cell).tolist() == gather.dedup_border_numpy(allr, owner, cell).tolist()
+
+
 def test_dedup_single_rank_is_identity():
     rng = np.random.default_rng(1)
     r = _make(50, 0, rng)
