@@ -184,3 +184,33 @@ def test_live_reference_radial_undistortion(r):
             assert np.array_equal(orc.image(i, lvl), rs.image(i, lvl)), (i, lvl)
     # r == 0 is the identity (Image::load does not call undistort then, Image.cpp:51)
     assert np.array_equal(hio.undistort(sc.images[0], 300.0, 0.0), sc.images[0])
+
+
+@needs_ref
+def test_live_reference_config0_two_views(tmp_path):
+    # BASELINE.json configs[0]: tiny 2-view NVM, 16 seed points, the reference CPU path.  Known answer with the reference's defaults:
+    # no patch at all (MIN_IMAGES_PER_PATCH = 3, Scene.cpp:128) - asked of the reference's own command line; with the explicit override
+    # MIN_IMAGES_PER_PATCH = 2 (and the 2-view covisibility the 50-point threshold can never produce from 16 points) the reference's
+    # PatchOptimizer and the oracle agree bit for bit.
+    sc = hp.synth.plane_scene(n_views=2, width=640, height=480, focal=600.0, radius=6.08, arc_deg=18.9, n_seeds=16,
+                              extent=0.5, seed=1, tex_size=256, depth_noise=0.0)
+    nvm = str(tmp_path / "scene.nvm")
+    hp.synth.write_nvm(sc, nvm)
+    r = ref.run_cli(nvm, str(tmp_path / "out"), threads=1)
+    assert r.returncode == 0, r.stderr[-1000:]
+    final = open(tmp_path / "out" / "patches-final.ply").read()
+    assert "element vertex 0" in final
+    opt2 = oracle.Options.defaults(min_images_per_patch=2)
+    orc = oracle.OracleScene.from_synth(sc, opt2)
+    rs = ref.RefScene(nvm, opt2)
+    assert rs.covis() == orc.covis() == [[], []]
+    seeds, valid = orc.seed_patches(sc.points, sc.meas_offsets, sc.meas_cam)
+    assert valid.sum() == 16
+    seeds = np.ascontiguousarray(seeds[valid])
+    a = orc.optimize_batch(seeds)
+    b = rs.optimize_batch(seeds)
+    assert np.array_equal(a["status"] == 0, b["status"] == 0)
+    ok = b["status"] == 0
+    assert ok.sum() >= 8                                   # addImages adds nothing (empty covisibility); two views suffice with the override
+    for f in ("center", "normal", "color", "nimages", "images"):
+        assert np.array_equal(a[f][ok], b[f][ok]), f
