@@ -111,8 +111,7 @@ struct KernelVariant {
     size_t smem;
 };
 #define HP_VARIANT(OW, SW, LPW) {OW, SW, LPW, hp::optimize_kernel<OW, SW, LPW>, sizeof(hp::CtaSharedT<OW, SW, LPW>)}
-static const KernelVariant g_variants[] = {HP_VARIANT(2, 10, 32), HP_VARIANT(2, 8, 32), HP_VARIANT(2, 6, 32), HP_VARIANT(2, 12, 32),
-                                           HP_VARIANT(4, 10, 16), HP_VARIANT(1, 8, 32)};
+static const KernelVariant g_variants[] = {HP_VARIANT(2, 10, 32), HP_VARIANT(2, 12, 32)};   // other shapes measured: profiles/r1_*
 static const int g_default_variant = 0;
 
 // parked-slot variant of the same kernel (patch state pools in HBM/L2): used when a batch has more patches than the
@@ -123,7 +122,7 @@ struct ParkedVariant {
     size_t smem;
 };
 #define HP_PVARIANT(OW, SW, LPW) {OW, SW, LPW, hp::optimize_kernel_parked<OW, SW, LPW>, sizeof(hp::CtaSharedP<OW, SW, LPW>)}
-static const ParkedVariant g_pvariants[] = {HP_PVARIANT(2, 10, 32), HP_PVARIANT(2, 12, 32), HP_PVARIANT(4, 10, 16)};
+static const ParkedVariant g_pvariants[] = {HP_PVARIANT(2, 10, 32)};
 static const int g_default_pvariant = 0;
 
 static int ensure_patch_capacity(hpmvs_engine* e, size_t n) {

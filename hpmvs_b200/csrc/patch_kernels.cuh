@@ -129,10 +129,6 @@ struct __align__(16) LaneCtx {
     unsigned short images[MAXV];         // pImages_
 };
 
-struct __align__(16) WarpShared {
-    Scratch S;
-    LaneCtx ctx[32];
-};
 // one warp of the stand-alone scoring kernel (K1): 7 KB, so that 28 warps are resident per SM
 struct __align__(16) NccWarp {
     Scratch S;
