@@ -209,11 +209,25 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": "patches/s", "cores": threads, "kind": kind,
                              "sample": f"first {sample} of {len(seeds)} seed patches per step; {how}"},
             "e2e": {"value": val, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _OUT.write(json.dumps(line) + "\n"); _OUT.flush()
+
+
+_OUT = sys.stdout
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: keep a private handle on the real stdout and point fd 1 at stderr, so that whatever
+    libraries print there (NCCL's version banner, OpenMP notices ...) cannot end up next to it."""
+    real = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    return real
 
 
 def main():
     args = parse_args()
+    global _OUT
+    _OUT = _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -428,7 +442,7 @@ def main():
                                  "patch_scores_per_s": nb / ncc_launch_s, "traffic": None,
                                  "note": "secondary figure: the scoring part of the path alone; issue-bound (see profiles/), not counted in value/e2e"},
                 "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        _OUT.write(json.dumps(line) + "\n"); _OUT.flush()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -37,6 +37,18 @@ struct Driver {
 
     double width(int level) const { return p->root_width / (double)(1 << level); }
 
+    // multi-GPU: the cells of tree level `shard_level` are dealt out to `shard_count` ranks; a rank only keeps patches in its own cells
+    // (the reference hands a patch that leaves a sub-tree to the neighbouring CellProcessor, CellProcessor.cpp:147-153, 487-540; here
+    // the neighbouring rank grows its side from its own seeds and the final gather + hpmvs_dedup_border merges the borders)
+    bool mine(const float* c) const {
+        if (p->shard_count <= 1) return true;
+        const double w = width(p->shard_level);
+        int64_t k[3];
+        for (int i = 0; i < 3; i++) k[i] = (int64_t)std::floor(((double)c[i] - origin[i]) / w);
+        const int64_t cell = (k[0] * 73856093ll) ^ (k[1] * 19349663ll) ^ (k[2] * 83492791ll);
+        return (int)(((cell % p->shard_count) + p->shard_count) % p->shard_count) == p->shard_rank;
+    }
+
     int64_t key_of(const float* c, double w) const {
         int64_t k[3];
         for (int i = 0; i < 3; i++) k[i] = (int64_t)std::floor(((double)c[i] - origin[i]) / w) + ((int64_t)1 << 20);
@@ -99,6 +111,7 @@ struct Driver {
         for (size_t i = 0; i < out.size(); i++) {
             if (out[i].status != HPMVS_OK) continue;
             if (norm3f(out[i].center, seeds[i].center) > out[i].scale * 2) continue;             // Scene.cpp:171
+            if (!mine(out[i].center)) continue;
             first.push_back(out[i]);
         }
         Recs cells;
@@ -141,6 +154,7 @@ struct Driver {
                         const double rel = ((double)r.center[a] - origin[a]) / p->root_width;
                         good = rel >= 0.0 && rel < 1.0;
                     }
+                    good = good && mine(r.center);
                     const int nimg = r.nimages > 1 ? r.nimages : 1;
                     good = good && counts[3 * i] >= MIN_IMAGES && counts[3 * i + 1] < MIN_IMAGES;
                     good = good && counts[3 * i + 2] >= MIN_IMAGES - 1 && (counts[3 * i + 2] * 1.0 / nimg > 0.75);
@@ -198,7 +212,9 @@ extern "C" {
 int hpmvs_pipeline_run(hpmvs_engine_t* e, const hpmvs_pipeline_params_t* params, int nseeds, const hpmvs_patch_t* seeds,
                        hpmvs_patch_t** out, int* nout, hpmvs_pipeline_stats_t* stats) {
     if (!e || !params || !out || !nout || nseeds < 0 || (nseeds > 0 && !seeds) || !params->cams || params->ncams <= 0 ||
-        params->start_level < 0 || params->final_level < params->start_level || params->final_level > 20 || !(params->root_width > 0.0))
+        params->start_level < 0 || params->final_level < params->start_level || params->final_level > 20 || !(params->root_width > 0.0) ||
+        (params->shard_count > 1 && (params->shard_rank < 0 || params->shard_rank >= params->shard_count || params->shard_level < 0 ||
+                                     params->shard_level > params->start_level)))
         return HPMVS_E_ARG;
     Driver d;
     d.e = e; d.p = params;

@@ -209,8 +209,9 @@ class WavefrontDriver:
 # The same driver in C++ behind the C ABI (hpmvs_pipeline_run, hpmvs_b200/csrc/host_pipeline.cpp): the product's host path.
 # ----------------------------------------------------------------------------------------------------------------------
 def run_native(engine, seeds: np.ndarray, origin, root_width: float, start_level: int, final_level: int, final_min_level: int = 9,
-               max_rounds: int = 64, dedup_ref_pixel: bool = True):
-    """Runs hpmvs_pipeline_run on `engine`; returns (final patch records, PipelineStats)."""
+               max_rounds: int = 64, dedup_ref_pixel: bool = True, shard_count: int = 1, shard_rank: int = 0, shard_level: int = 0):
+    """Runs hpmvs_pipeline_run on `engine`; returns (final patch records, PipelineStats).  shard_count > 1: only the cells of tree
+    level shard_level that are dealt to shard_rank are grown (one call per GPU; merge with gather.gather_patches + dedup_border)."""
     import ctypes as C
     from . import engine as E
     L = E._lib()
@@ -218,7 +219,7 @@ def run_native(engine, seeds: np.ndarray, origin, root_width: float, start_level
     class Params(C.Structure):
         _fields_ = [("origin", C.c_double * 3), ("root_width", C.c_double), ("start_level", C.c_int32), ("final_level", C.c_int32),
                     ("final_min_level", C.c_int32), ("max_rounds", C.c_int32), ("dedup_ref_pixel", C.c_int32), ("ncams", C.c_int32),
-                    ("cams", C.POINTER(E.Camera))]
+                    ("cams", C.POINTER(E.Camera)), ("shard_count", C.c_int32), ("shard_rank", C.c_int32), ("shard_level", C.c_int32)]
 
     class Stats(C.Structure):
         _fields_ = [("optimize_calls", C.c_int64), ("optimized_ok", C.c_int64), ("seconds_optimize", C.c_double), ("seconds_accept", C.c_double),
@@ -226,7 +227,7 @@ def run_native(engine, seeds: np.ndarray, origin, root_width: float, start_level
 
     cams = (E.Camera * len(engine.cameras))(*engine.cameras)
     prm = Params((C.c_double * 3)(*[float(v) for v in origin]), float(root_width), start_level, final_level, final_min_level, max_rounds,
-                 1 if dedup_ref_pixel else 0, len(engine.cameras), cams)
+                 1 if dedup_ref_pixel else 0, len(engine.cameras), cams, shard_count, shard_rank, shard_level)
     st = Stats()
     s = np.ascontiguousarray(seeds)
     assert s.dtype == E.PATCH_DTYPE

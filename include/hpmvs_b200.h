@@ -192,6 +192,9 @@ typedef struct hpmvs_pipeline_params {
     int32_t dedup_ref_pixel;       /* != 0: one accepted candidate per reference-view image cell and round */
     int32_t ncams;
     const hpmvs_camera_t *cams;    /* the cameras the engine was given (candidate construction runs on the host) */
+    int32_t shard_count;           /* multi-GPU: > 1 = this call grows only the cells of tree level shard_level dealt to shard_rank; */
+    int32_t shard_rank;            /*   0 or 1 = everything.  Merge the ranks' results with an NCCL gather + hpmvs_dedup_border. */
+    int32_t shard_level;           /*   (<= start_level) */
 } hpmvs_pipeline_params_t;
 typedef struct hpmvs_pipeline_stats {
     int64_t optimize_calls, optimized_ok;
