@@ -73,3 +73,34 @@ def test_nvm_round_trip(tmp_path):
     txt = open(path).read().split()
     assert txt[0] == "NVM_V3" and int(txt[1]) == 3
     assert os.path.getsize(str(tmp_path / sc.cameras[0].filename)) == len(b"P6\n64 48\n255\n") + 64 * 48 * 3
+
+
+def test_host_entry_points_reject_bad_arguments():
+    # no GPU needed: the host-side entry points validate before they touch a device
+    lib = C.CDLL(_native.build())
+    lib.hpmvs_dedup_border.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    lib.hpmvs_undistort_rgb.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+    lib.hpmvs_pipeline_run.argtypes = [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 4
+    assert lib.hpmvs_dedup_border(-1, None, None, 1.0, None) < 0
+    assert lib.hpmvs_dedup_border(3, None, None, 1.0, None) < 0
+    assert lib.hpmvs_dedup_border(0, None, None, 0.0, None) < 0          # cell edge must be positive
+    assert lib.hpmvs_dedup_border(0, None, None, 1.0, None) == 0         # empty input is fine
+    assert lib.hpmvs_undistort_rgb(None, 4, 4, 100.0, 0.1, None, None) < 0
+    img = np.zeros((4, 4, 3), np.uint8)
+    assert lib.hpmvs_undistort_rgb(img.ctypes.data, 0, 4, 100.0, 0.1, img.ctypes.data, None) < 0
+    assert lib.hpmvs_pipeline_run(None, None, 0, None, None, None, None) < 0
+    lib.hpmvs_free(None)                                                 # free(NULL) is a no-op
+
+
+def test_undistort_identity_and_mask():
+    from hpmvs_b200 import io as hio
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (40, 60, 3), dtype=np.uint8)
+    same, written = hio.undistort(img, 80.0, 0.0, return_mask=True)
+    assert np.array_equal(same, img) and written.all()
+    und, written = hio.undistort(img, 80.0, 0.05, return_mask=True)
+    assert und.shape == img.shape and 0.5 < written.mean() < 1.0 and (und[~written] == 0).all()
+    # a constant image stays constant wherever it is written (bilinear weights sum to one; f32 -> u8 truncation of an exact value)
+    flat = np.full((40, 60, 3), 77, np.uint8)
+    und, written = hio.undistort(flat, 80.0, -0.04, return_mask=True)
+    assert (und[written] == 77).all()
