@@ -408,6 +408,13 @@ def main():
                 traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"])
         except Exception:
             traffic = None
+        ncc_traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload + "_ncc")
+            if tj:
+                ncc_traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"])
+        except Exception:
+            ncc_traffic = None
         # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
         cpu = None
         if world == 1:
@@ -439,7 +446,7 @@ def main():
                                  "peak": peak, "unit": "GB/s",
                                  "frac": (TEX_BYTES * ncc_tex_per_launch + (REC_BYTES + 4 * hp.MAX_VIEWS) * nb) / ncc_launch_s / 1e9 / peak,
                                  "patches_per_launch": int(nb), "textures_per_launch": ncc_tex_per_launch, "launch_ms": 1e3 * ncc_launch_s,
-                                 "patch_scores_per_s": nb / ncc_launch_s, "traffic": None,
+                                 "patch_scores_per_s": nb / ncc_launch_s, "traffic": ncc_traffic,
                                  "note": "secondary figure: the scoring part of the path alone; issue-bound (see profiles/), not counted in value/e2e"},
                 "cpu_baseline": cpu}
         _OUT.write(json.dumps(line) + "\n"); _OUT.flush()
