@@ -214,3 +214,38 @@ def test_live_reference_config0_two_views(tmp_path):
     assert ok.sum() >= 8                                   # addImages adds nothing (empty covisibility); two views suffice with the override
     for f in ("center", "normal", "color", "nimages", "images"):
         assert np.array_equal(a[f][ok], b[f][ok]), f
+
+
+@needs_ref
+@pytest.mark.parametrize("views,arc,overrides", [
+    (12, 110.0, {}),                                                                       # wide baseline: angle filters, view sorting
+    (20, 70.0, {}),                                                                        # long view lists (up to 18 views per patch)
+    (6, 36.0, dict(ncc_alpha_1=0.2, ncc_alpha_2=0.7, min_images_per_patch=2)),           # HpmvsOptions overrides
+    (8, 40.0, dict(max_angle=float(np.float32(np.pi / 4)), maxlevel=4, start_level=3)),    # fewer pyramid levels, tighter angle gate
+])
+def test_live_reference_option_and_view_sweep(views, arc, overrides):
+    sc = hp.synth.plane_scene(n_views=views, width=320, height=240, focal=300.0, arc_deg=arc, n_seeds=200, seed=30 + views, tex_size=256)
+    opt = oracle.Options.defaults(**overrides)
+    orc = oracle.OracleScene.from_synth(sc, opt)
+    rs = ref.RefScene.from_synth(sc, opt)
+    for i in range(rs.n_cameras):
+        assert bytes(orc.camera(i)) == bytes(rs.camera(i))
+    assert orc.covis() == rs.covis()
+    seeds, valid = orc.seed_patches(sc.points, sc.meas_offsets, sc.meas_cam)
+    seeds = np.ascontiguousarray(seeds[valid])
+    rng = np.random.default_rng(views)
+    h = len(seeds) // 2                                                                    # half of them knocked off the surface
+    seeds["center"][:h, :3] += rng.normal(0, 0.03, (h, 3)).astype(np.float32)
+    n = seeds["normal"][:h, :3] + rng.normal(0, 0.25, (h, 3)).astype(np.float32)
+    seeds["normal"][:h, :3] = n / np.linalg.norm(n, axis=1, keepdims=True)
+    a = orc.optimize_batch(seeds, nthreads=4)
+    b = rs.optimize_batch(seeds, nthreads=4)
+    ok = b["status"] == 0
+    assert np.array_equal(a["status"] == 0, ok) and ok.sum() >= 10
+    for f in ("center", "normal", "color", "nimages", "images"):
+        assert np.array_equal(a[f][ok], b[f][ok]), f
+    orc.depth_reset(); rs.depth_reset()
+    orc.depth_set(a); rs.depth_set(b)
+    for lvl in range(opt.maxlevel + 1):
+        assert np.array_equal(orc.depth(0, lvl), rs.depth(0, lvl))
+    assert np.array_equal(orc.accept(a[ok], 1.0), rs.accept(b[ok], 1.0))
