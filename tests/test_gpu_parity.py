@@ -222,6 +222,37 @@ def test_config1_full_size_against_the_reference_path():
     assert dc.max() < OUTLIER_CENTER
 
 
+@pytest.mark.parametrize("views,arc,overrides", [
+    (20, 70.0, {}),                                                                        # up to 18 views per patch: several texture groups per evaluation
+    (12, 110.0, {}),                                                                       # wide baseline: angle filters, view sorting
+    (6, 36.0, dict(ncc_alpha_1=0.2, ncc_alpha_2=0.7, min_images_per_patch=2)),           # HpmvsOptions overrides
+    (8, 40.0, dict(max_angle=float(np.float32(np.pi / 4)), maxlevel=4, start_level=3)),    # fewer pyramid levels, tighter angle gate
+])
+def test_view_count_and_option_sweep_bit_exact(views, arc, overrides):
+    """The sweep of tests/test_reference_golden.py (there: oracle == reference build) on the engine, start mode 0 against the oracle's
+    correctly rounded asinf: every field bit-exact, including evaluation and texture counts."""
+    sc = hp.synth.plane_scene(n_views=views, width=320, height=240, focal=300.0, arc_deg=arc, n_seeds=200, seed=30 + views, tex_size=256)
+    orc = oracle.OracleScene.from_synth(sc, oracle.Options.defaults(**overrides))
+    eng = hp.Engine.from_synth(sc, hp.Options.defaults(**overrides))
+    seeds, valid = orc.seed_patches(sc.points, sc.meas_offsets, sc.meas_cam)
+    seeds = np.ascontiguousarray(seeds[valid])
+    rng = np.random.default_rng(views)
+    h = len(seeds) // 2
+    seeds["center"][:h, :3] += rng.normal(0, 0.03, (h, 3)).astype(np.float32)
+    n = seeds["normal"][:h, :3] + rng.normal(0, 0.25, (h, 3)).astype(np.float32)
+    seeds["normal"][:h, :3] = n / np.linalg.norm(n, axis=1, keepdims=True)
+    oracle.set_cr_asinf(True)
+    try:
+        ref = orc.optimize_batch(seeds, nthreads=8)
+    finally:
+        oracle.set_cr_asinf(False)
+    got = eng.optimize(to_engine(seeds))
+    st = compare_outputs(ref, got)
+    assert st["status_equal"] == st["n"], st
+    assert st["vis_equal"] == st["both_ok"] and st["bit_exact"] == st["both_ok"] and st["both_ok"] >= 10, {k: v for k, v in st.items() if not hasattr(v, "shape")}
+    assert np.array_equal(ref["evals"], got["evals"]) and np.array_equal(ref["textures"], got["textures"])
+
+
 def test_edge_cases(plane):
     sc, orc, seeds, eng = plane
     # empty batch
