@@ -253,6 +253,9 @@ void hpmvs_engine_destroy(hpmvs_engine_t* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
+    // batches submitted on caller streams (hpmvs_optimize_batch_submit / _device) may still be running on our buffers
+    for (int i = 0; i < HP_RING; i++) if (e->slot_done[i]) cudaEventSynchronize(e->slot_done[i]);
+    for (auto& st : e->stage2) if (st.done) cudaEventSynchronize(st.done);
     for (auto& cam : e->images)
         for (auto& li : cam)
             if (li.data) cudaFree(li.data);
