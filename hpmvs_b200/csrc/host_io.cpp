@@ -12,6 +12,7 @@
 #include <cmath>
 #include <complex>
 #include <fstream>
+#include <iomanip>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -110,6 +111,35 @@ int hpmvs_nvm_points(const hpmvs_nvm_t* m, double* xyz, double* rgb, int32_t* of
     if (meas_feat) std::copy(m->meas_feat.begin(), m->meas_feat.end(), meas_feat);
     if (meas_xy) std::copy(m->meas_xy.begin(), m->meas_xy.end(), meas_xy);
     return 0;
+}
+
+// NVMReader::saveNVM (src/hpmvs/NVMReader.cpp:157-183) for the model that was read: 12 significant digits, the stream operators of
+// NVM_Model / NVM_Camera / NVM_Point / NVM_Measurement (:34-111: colours as integers, a blank before every measurement field), the
+// terminating empty model "0" without a newline
+int hpmvs_nvm_write(const hpmvs_nvm_t* m, const char* path) {
+    if (!m || !path) return HPMVS_E_ARG;
+    std::ofstream out(path);
+    if (!out.good()) return HPMVS_E_ARG;
+    out << std::setprecision(12);
+    out << "NVM_V3" << std::endl;
+    const int ncam = (int)m->cams.size(), npts = (int)m->offsets.size() - 1;
+    out << std::endl << ncam << std::endl;
+    for (const auto& c : m->cams) {
+        out << c.filename << " " << c.f << " " << c.q[0] << " " << c.q[1] << " " << c.q[2] << " " << c.q[3] << " "
+            << c.c[0] << " " << c.c[1] << " " << c.c[2] << " " << c.r << " " << 0 << std::endl;
+    }
+    if (ncam > 0) out << std::endl << npts << std::endl;
+    for (int i = 0; i < npts; i++) {
+        out << m->xyz[3 * i] << " " << m->xyz[3 * i + 1] << " " << m->xyz[3 * i + 2] << " " << (int)m->rgb[3 * i] << " "
+            << (int)m->rgb[3 * i + 1] << " " << (int)m->rgb[3 * i + 2];
+        const int a = m->offsets[i], b = m->offsets[i + 1];
+        out << " " << (b - a);
+        for (int k = a; k < b; k++)
+            out << " " << m->meas_cam[k] << " " << m->meas_feat[k] << " " << m->meas_xy[2 * k] << " " << m->meas_xy[2 * k + 1];
+        out << std::endl;
+    }
+    out << "0";
+    return out.good() ? 0 : HPMVS_E_ARG;
 }
 
 // binary PPM; returns the size with rgb == NULL, fills rgb (3*w*h bytes, interleaved) otherwise

@@ -68,6 +68,18 @@ def read_nvm(path: str, fix_path: bool = True, load_images: bool = True) -> Synt
     return SynthScene(os.path.basename(path), cams, images, xyz, offs, mc[:nm])
 
 
+def rewrite_nvm(src: str, dst: str, fix_path: bool = True) -> None:
+    """Read an NVM_V3 file and write it back the way NVMReader::saveNVM does (NVMReader.cpp:157-183)."""
+    L = _lib()
+    L.hpmvs_nvm_write.argtypes = [C.c_void_p, C.c_char_p]
+    h = C.c_void_p()
+    _check(L.hpmvs_nvm_open(src.encode(), 1 if fix_path else 0, C.byref(h)))
+    try:
+        _check(L.hpmvs_nvm_write(h, dst.encode()))
+    finally:
+        L.hpmvs_nvm_close(h)
+
+
 def undistort(rgb: np.ndarray, f: float, r: float, return_mask: bool = False):
     """Image::undistort (Image.cpp:68-149) on an [h, w, 3] u8 image; r == 0 returns a copy.  return_mask: also the [h, w] bool mask of
     the pixels that were written (the others are 0 here and uninitialised memory in the reference)."""

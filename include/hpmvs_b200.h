@@ -253,6 +253,8 @@ int  hpmvs_nvm_camera(const hpmvs_nvm_t *m, int i, char *filename, int cap, doub
 /* any output pointer may be NULL; offsets has num_points+1 entries (CSR over the measurement arrays) */
 int  hpmvs_nvm_points(const hpmvs_nvm_t *m, double *xyz, double *rgb, int32_t *offsets, int32_t *meas_cam,
                       int32_t *meas_feat, double *meas_xy);
+/* Replaces mo3d::NVMReader::saveNVM (src/hpmvs/NVMReader.cpp:157-183) for the model held by `m`: same text, byte for byte. */
+int  hpmvs_nvm_write(const hpmvs_nvm_t *m, const char *path);
 /* Replaces Image::undistort (src/hpmvs/Image.cpp:68-149): undoes VisualSFM's radial distortion `r` (NVM camera line, NVMReader.cpp:70)
  * on an interleaved u8 RGB level-0 image with focal length f, before the pyramid is built; r == 0 copies.  Host function (same libm
  * as the reference for its pow / complex pow), bit-exact against the reference build incl. the f32 -> u8 truncation.  Target pixels

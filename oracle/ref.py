@@ -54,6 +54,7 @@ def lib():
         L.refh_scene_load.restype = vp; L.refh_scene_load.argtypes = [C.c_char_p, C.POINTER(Options)]
         L.refh_scene_free.argtypes = [vp]
         L.refh_num_cameras.argtypes = [vp]; L.refh_num_points.argtypes = [vp]
+        L.refh_save_nvm.argtypes = [vp, C.c_char_p]
         L.refh_get_camera.argtypes = [vp, C.c_int, C.POINTER(Camera)]
         L.refh_get_image.argtypes = [vp, C.c_int, C.c_int, u8p, C.c_int, ip, ip]
         L.refh_get_covis.argtypes = [vp, C.c_int, ip, C.c_int]
@@ -95,6 +96,10 @@ class RefScene:
         path = os.path.join(tmp.name, "scene.nvm")
         hp.synth.write_nvm(scene, path)
         return cls(path, options, _tmp=tmp)
+
+    def save_nvm(self, path: str) -> None:
+        """NVMReader::saveNVM of the loaded model."""
+        lib().refh_save_nvm(self._h, path.encode())
 
     @property
     def n_cameras(self) -> int:

@@ -74,6 +74,12 @@ void* refh_scene_load(const char* nvm_path, const orc_options_t* opt) {
 
 void refh_scene_free(void* h) { delete static_cast<RefScene*>(h); }
 
+// NVMReader::saveNVM (NVMReader.cpp:157-183) of the model that was loaded
+void refh_save_nvm(void* h, const char* path) {
+    std::vector<mo3d::NVM_Model> models(1, static_cast<RefScene*>(h)->model);
+    mo3d::NVMReader::saveNVM(path, models);
+}
+
 int refh_num_cameras(void* h) { return (int)static_cast<RefScene*>(h)->scene.cameras_.size(); }
 int refh_num_points(void* h) { return (int)static_cast<RefScene*>(h)->model.points.size(); }
 

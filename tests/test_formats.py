@@ -145,3 +145,20 @@ def test_reference_cli_reads_our_nvm_and_its_ply_round_trips(tmp_path):
     hio.write_ext_ply(str(tmp_path / "ours_light.ply"), rec, binary=True, normal=False, scale=False, visibility=False)
     mine = open(str(tmp_path / "ours_light.ply"), "rb").read()
     assert light[:light.index(b"end_header")] == mine[:mine.index(b"end_header")] and len(light) == len(mine)
+
+
+def test_nvm_writer_matches_the_reference_saveNVM(tmp_path):
+    from oracle import ref
+    if not ref.available():
+        import pytest
+        pytest.skip("oracle/_ref/libhpmvs_ref.so not built (needs /root/reference)")
+    sc = hp.synth.plane_scene(n_views=4, width=96, height=64, focal=80.0, n_seeds=40, seed=9, tex_size=64)
+    sc.cameras[1].r = -0.0123
+    src = str(tmp_path / "scene.nvm")
+    hp.synth.write_nvm(sc, src)
+    theirs, ours = str(tmp_path / "theirs.nvm"), str(tmp_path / "ours.nvm")
+    ref.RefScene(src).save_nvm(theirs)                      # mo3d::NVMReader::readFile + saveNVM
+    hio.rewrite_nvm(src, ours)                              # hpmvs_nvm_open + hpmvs_nvm_write
+    assert open(ours, "rb").read() == open(theirs, "rb").read()
+    back = hio.read_nvm(ours, load_images=False)            # and it reads back
+    assert len(back.cameras) == 4 and back.points.shape == (40, 3)
