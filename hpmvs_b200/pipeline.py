@@ -66,10 +66,12 @@ def _pack(keys: np.ndarray) -> np.ndarray:
 
 class WavefrontDriver:
     def __init__(self, backend, origin, root_width: float, start_level: int, final_level: int, max_rounds: int = 64,
-                 final_min_level: int = 9, cameras=None):
+                 final_min_level: int = 9, cameras=None, shard_count: int = 1, shard_rank: int = 0, shard_level: int = 0):
         # final_min_level = HpmvsOptions::PATCH_FINAL_MINLEVEL as the CLI sets it (src/main.cpp:44,234): a cell below that tree
         # level whose patch yields no child when it branches is split anyway and loses its patch (CellProcessor.cpp:266-283)
         self.final_min_level = final_min_level
+        # multi-GPU: the cells of tree level shard_level are dealt to shard_count ranks, this driver keeps only shard_rank's (host_pipeline.cpp)
+        self.shard_count, self.shard_rank, self.shard_level = shard_count, shard_rank, shard_level
         # cameras (hpmvs_camera_t list, optional): enables the per-round image-space de-duplication below
         self.P0 = None
         if cameras is not None:
@@ -105,6 +107,13 @@ class WavefrontDriver:
                 live[i] = True
         return live
 
+    def _mine(self, centers: np.ndarray) -> np.ndarray:
+        if self.shard_count <= 1:
+            return np.ones(len(centers), bool)
+        k = _cell_keys(centers, self.origin, self.width(self.shard_level))
+        cell = (k[:, 0] * 73856093) ^ (k[:, 1] * 19349663) ^ (k[:, 2] * 83492791)
+        return np.mod(cell, self.shard_count) == self.shard_rank
+
     def _first_per_ref_pixel(self, rec: np.ndarray, width: float) -> np.ndarray:
         """The reference commits one patch at a time, so a patch that has just been accepted occupies its depth-map pixels and blocks
         the next candidate that lands on them (pixelFreeTests, Scene.cpp:587-611).  A batched round tests all candidates against the
@@ -130,6 +139,7 @@ class WavefrontDriver:
         ok = out["status"] == 0
         moved = np.linalg.norm(out["center"][:, :3] - seeds["center"][:, :3], axis=1)
         ok &= ~(moved > out["scale"] * 2)                                    # Scene.cpp:171
+        ok &= self._mine(out["center"])
         cells: Dict[int, np.ndarray] = {}
         level = self.start_level
         first = out[ok]
@@ -163,6 +173,7 @@ class WavefrontDriver:
                 # (CellProcessor.cpp:147-153, distributeBorderCell :533-540): the cloud never grows beyond the octree's root
                 rel = (res["center"][:, :3].astype(np.float64) - self.origin) / self.root_width
                 good &= ((rel >= 0.0) & (rel < 1.0)).all(axis=1)
+                good &= self._mine(res["center"])
                 t = time.perf_counter()
                 counts = self.b.accept(res, DEPTH_TEST_FACTOR)
                 self.stats.seconds_accept += time.perf_counter() - t

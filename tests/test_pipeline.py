@@ -89,8 +89,8 @@ def test_native_driver_equals_python_driver():
     seeds, valid = hp.seed_patches(eng.options, eng.cameras, sc.points, sc.meas_offsets, sc.meas_cam)
     seeds = np.ascontiguousarray(seeds[valid])
     width0 = float(np.median(seeds["scale"])) * 2.2
-    for fml in (0, 8):
-        args = dict(origin=(-8.0, -8.0, -8.0), root_width=width0 * 64, start_level=6, final_level=8, final_min_level=fml)
+    for fml, shard in ((0, {}), (8, {}), (8, dict(shard_count=3, shard_rank=1, shard_level=4))):
+        args = dict(origin=(-8.0, -8.0, -8.0), root_width=width0 * 64, start_level=6, final_level=8, final_min_level=fml, **shard)
         d = pipeline.WavefrontDriver(pipeline.EngineBackend(eng), cameras=eng.cameras, **args)
         want = d.run(seeds)
         got, st = pipeline.run_native(eng, seeds, dedup_ref_pixel=True, **args)
