@@ -26,7 +26,18 @@ REF_ROOT = "/root/reference"
 FAIL = 100   # status of a patch for which the reference's optimize() returned false
 
 
+_tried_build = False
+
+
 def available() -> bool:
+    """True when oracle/_ref/libhpmvs_ref.so exists; where the reference's sources are present it is built on first use."""
+    global _tried_build
+    if not os.path.exists(LIB_PATH) and not _tried_build and os.path.isdir(os.path.join(REF_ROOT, "src", "hpmvs")):
+        _tried_build = True
+        try:
+            build()
+        except Exception:
+            pass
     return os.path.exists(LIB_PATH)
 
 
@@ -38,7 +49,7 @@ def build() -> Optional[str]:
         if os.path.exists(os.path.join(_HERE, "..", "hpmvs_b200", "libhpmvs_b200.so")):
             # the reference's CLI linked against the engine instead of its own PatchOptimizer.cpp (integration/)
             subprocess.run(["make", "-C", _HERE, "dropin"], check=True, capture_output=True)
-    return LIB_PATH if available() else None
+    return LIB_PATH if os.path.exists(LIB_PATH) else None
 
 
 _lib = None
