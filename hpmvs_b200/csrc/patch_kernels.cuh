@@ -1455,7 +1455,7 @@ __device__ __forceinline__ float full_depth(const DevCamera& cam, int xx, int yy
     return depth;
 }
 
-// Scene::depthTest with neighbours = true (Scene.cpp:534-585); `abs(diff)` is the C int abs (quirk Q18)
+// Scene::depthTest with neighbours = true (Scene.cpp:534-585); `abs(diff)` is float std::abs(float) with Eigen's include chain (see oracle/shim/Eigen/Dense)
 __device__ __forceinline__ bool depth_test(const DevCamera& cam, f4 c, f4 nrm, float scale, float margin, bool viewBlock) {
     const f3 imgC = mult_pt(cam, c, 0);
     const int ix0 = round_px(imgC.x, imgC.z) - 1, iy0 = round_px(imgC.y, imgC.z) - 1;
@@ -1470,7 +1470,7 @@ __device__ __forceinline__ bool depth_test(const DevCamera& cam, f4 c, f4 nrm, f
             const float imgDepth = full_depth(cam, ix, iy);
             if (imgDepth >= MAX_DEPTH) { if (viewBlock) return false; else continue; }
             const float diff = imgDepth - depth;
-            if (!viewBlock) { if (!((double)abs((int)diff) < thr)) return false; }
+            if (!viewBlock) { if (!((double)fabsf(diff) < thr)) return false; }
             else { if (!((double)diff > thr)) return false; }
         }
     return true;

@@ -692,8 +692,8 @@ float get_depth_at_level(const Scene& s, int img, int xx, int yy, int level) {
 }
 
 // Scene::depthTest(patch, ix, iy, depth, image, margin, viewBlock) (Scene.cpp:558-585).
-// NOTE `abs(diff)` there is the C library's int abs(int): Scene.cpp only sees <cmath>/<cstdlib> declarations, so the
-// float argument is truncated to int first (quirk Q18; checked with g++ 13 on the same include set).
+// NOTE `abs(diff)` there is float std::abs(float): real Eigen/Core includes <emmintrin.h> -> <mm_malloc.h> -> <stdlib.h>, whose
+// libstdc++ wrapper does `using std::abs` (checked with g++ 13; round 1 had restated the C int abs(int) - former quirk Q18, withdrawn).
 bool depth_test_px(const Scene& s, const orc_patch_t& p, int ix, int iy, float depth, int image, float margin, bool viewBlock) {
     if (depth < 0 || ix < 0 || ix >= s.images[image].w[0] || iy < 0 || iy >= s.images[image].h[0]) return false;
     const float imgDepth = get_full_depth(s, image, ix, iy);
@@ -703,7 +703,7 @@ bool depth_test_px(const Scene& s, const orc_patch_t& p, int ix, int iy, float d
     const V4 ray = normalized4(sub4(c, s.cameras[image].center));
     const float diff = imgDepth - depth;
     const float factor = std::min(2.0f, 2.0f + dot4(ray, n));
-    if (!viewBlock) return ::abs((int)diff) < p.scale * margin * factor * 2.0;
+    if (!viewBlock) return std::fabs(diff) < p.scale * margin * factor * 2.0;
     return diff > p.scale * margin * factor * 2.0;
 }
 

@@ -8,6 +8,7 @@ Bars (stated once, used below):
     differs by one ulp: >= 90 % of the patches stay bit-exact, >= 99 % agree within TOL_CENTER * scale / TOL_NORMAL /
     TOL_SCORE, and the rare patch whose optimiser slides along a flat valley of the objective stays within the OUTLIER_*
     bounds (the same spread the oracle shows between its own two asinf modes, tests/test_oracle.py)."""
+import ast
 import os
 
 import numpy as np
@@ -129,7 +130,7 @@ def test_optimize_vs_native_libm_within_tolerance(plane):
 
 def test_golden_fixture(plane):
     g = np.load(os.path.join(ROOT, "tests", "golden", "plane4_small.npz"))
-    kw = eval(str(g["scene_kwargs"]))
+    kw = ast.literal_eval(str(g["scene_kwargs"]))
     sc = hp.synth.plane_scene(**kw)
     import hashlib
     assert hashlib.sha256(np.stack(sc.images).tobytes()).hexdigest() == str(g["scene_sha256"])

@@ -6,6 +6,7 @@ HPMVS ships no golden vectors, so the oracle is pinned where 
   * analytic properties of the photometric pieces (NCC of a texture with itself = 1, pyramid of a constant image, ...);
   * the committed golden fixture tests/golden/plane4_small.npz (minted by tests/golden/make_golden.py from this
     oracle: a regression pin, not an external one)."""
+import ast
 import os
 
 import numpy as np
@@ -104,7 +105,7 @@ def test_optimize_converges_on_plane():
 
 def test_golden_fixture():
     g = np.load(os.path.join(ROOT, "tests", "golden", "plane4_small.npz"))
-    sc = hp.synth.plane_scene(**{k: (v.item() if hasattr(v, "item") else v) for k, v in eval(str(g["scene_kwargs"])).items()})
+    sc = hp.synth.plane_scene(**{k: (v.item() if hasattr(v, "item") else v) for k, v in ast.literal_eval(str(g["scene_kwargs"])).items()})
     import hashlib
     assert hashlib.sha256(np.stack(sc.images).tobytes()).hexdigest() == str(g["scene_sha256"]), "synthetic scene generator changed: regenerate the golden fixture"
     orc = oracle.OracleScene.from_synth(sc)

@@ -10,6 +10,7 @@ Two layers:
 Bar: bit-exact, every field.  Both sides evaluate std::asin(float) with this image's libm here (the engine's correctly
 rounded variant is compared in tests/test_gpu_parity.py and differs for the ~2 % of patches where glibc 2.39 is not
 correctly rounded)."""
+import ast
 import hashlib
 import os
 
@@ -26,7 +27,7 @@ FIXTURES = ["ref_plane6", "ref_city16"]
 
 def load_fixture(name):
     g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
-    kw = {k: (v.item() if hasattr(v, "item") else v) for k, v in eval(str(g["scene_kwargs"])).items()}
+    kw = {k: (v.item() if hasattr(v, "item") else v) for k, v in ast.literal_eval(str(g["scene_kwargs"])).items()}
     sc = getattr(hp.synth, str(g["generator"]))(**kw)
     assert hashlib.sha256(np.stack(sc.images).tobytes()).hexdigest() == str(g["scene_sha256"]), \
         "synthetic scene generator changed: regenerate with tests/golden/make_golden_ref.py"
