@@ -25,6 +25,7 @@
 #endif
 
 #include <math.h>
+#include <type_traits>
 
 // The loops below have tiny constant trip counts (3, 7, 10).  Fully unrolled, the state machine grows to >300 KB of
 // SASS and the kernel becomes instruction-fetch bound (ncu: 65% "no_instructions" stalls); kept rolled it fits the
@@ -64,7 +65,7 @@
 // The engine keeps every State in shared memory; telling the compiler lets it emit LDS/STS with immediate offsets
 // instead of generic loads plus address arithmetic.
 #if defined(__CUDA_ARCH__) && defined(BQ_STATE_IN_SHARED)
-#define BQ_ASSUME_SHARED(S) __builtin_assume(__isShared(&(S)))
+#define BQ_ASSUME_SHARED(S) do { if (!bq3::is_tile<typename std::remove_cv<typename std::remove_reference<decltype(S)>::type>::type>::value) __builtin_assume(__isShared(&(S))); else __builtin_assume(__isGlobal(&(S))); } while (0)
 #else
 #define BQ_ASSUME_SHARED(S)
 #endif
@@ -106,33 +107,83 @@ BQ_HD double dmin(double a, double b) { return a <= b ? a : b; }
 BQ_HD double dmax(double a, double b) { return a >= b ? a : b; }
 BQ_HD int hidx(int i, int j) { return j * (j + 1) / 2 + i; }  // i <= j
 
-struct State {
-    // problem (scaled space)
-    double xl[N], xu[N], scl[N];
-    double rhobeg, rhoend;
-    int maxeval, nevals;
-    // model
-    double xbase[N], xpt[NPT][N], fval[NPT], xopt[N], gopt[N], hq[NH], pq[NPT];
-    double bmat[NDIM][N], zmat[NPT][NPTM], sl[N], su[N], xnew[N], xalt[N], d[N], vlag[NDIM];
-    double w[3 * NDIM];
-    double x[N];  // current point in scaled space (what prelim/bobyqb call X)
-    // iteration scalars that live across evaluations
-    double rho, delta, diffa, diffb, diffc, dsq, crvmin, dnorm, distsq, adelt, alpha, cauchy, beta, denom;
-    double xoptsq, fsave, ratio, f, fbeg, stepa, stepb, vquad_r, fbase_r, minf;
-    int ntrits, itest, nfsav, nresc, kopt, kbase, knew, nf, kpt, pc, rc, nrem_r;
-    bool in_rescue_from_main;
-    int n_rescue;   // statistics only
+// Strided cells for the wavefront kernels (patch_kernels_wf.cuh): the states of 32 patches are interleaved in one "tile" - every
+// member of lane l's state is a cell of BQ_TILE_STRIDE bytes whose own value sits at byte offset 8*l, so that a warp whose lane l works
+// on slot l of a tile reads / writes 32 consecutive 8-byte words per access (one fully coalesced 256-byte request) and every member keeps
+// a compile-time offset from the lane's base pointer.  The cells behave like double / int in expressions; copies move the value only.
+#ifndef BQ_TILE_LANES
+#define BQ_TILE_LANES 32
+#endif
+struct alignas(8) SD {
+    double v;
+    double pad_[BQ_TILE_LANES - 1];
+    BQ_HD operator double() const { return v; }
+    BQ_HD SD& operator=(double x) { v = x; return *this; }
+    BQ_HD SD& operator=(const SD& o) { v = o.v; return *this; }
+    BQ_HD SD& operator+=(double x) { v += x; return *this; }
+    BQ_HD SD& operator-=(double x) { v -= x; return *this; }
+    BQ_HD SD& operator*=(double x) { v *= x; return *this; }
+    BQ_HD SD& operator/=(double x) { v /= x; return *this; }
 };
+struct alignas(8) SI {
+    int v;
+    int pad_[2 * BQ_TILE_LANES - 1];
+    BQ_HD operator int() const { return v; }
+    BQ_HD SI& operator=(int x) { v = x; return *this; }
+    BQ_HD SI& operator=(const SI& o) { v = o.v; return *this; }
+    BQ_HD SI& operator+=(int x) { v += x; return *this; }
+    BQ_HD SI& operator-=(int x) { v -= x; return *this; }
+    BQ_HD SI& operator++() { ++v; return *this; }
+    BQ_HD int operator++(int) { return v++; }
+    BQ_HD SI& operator--() { --v; return *this; }
+    BQ_HD int operator--(int) { return v--; }
+};
+
+template <class R, class I>
+struct StateT {
+    typedef R real;
+    typedef I integer;
+    // problem (scaled space)
+    R xl[N], xu[N], scl[N];
+    R rhobeg, rhoend;
+    I maxeval, nevals;
+    // model
+    R xbase[N], xpt[NPT][N], fval[NPT], xopt[N], gopt[N], hq[NH], pq[NPT];
+    R bmat[NDIM][N], zmat[NPT][NPTM], sl[N], su[N], xnew[N], xalt[N], d[N], vlag[NDIM];
+    R w[3 * NDIM];
+    R x[N];  // current point in scaled space (what prelim/bobyqb call X)
+    // iteration scalars that live across evaluations
+    R rho, delta, diffa, diffb, diffc, dsq, crvmin, dnorm, distsq, adelt, alpha, cauchy, beta, denom;
+    R xoptsq, fsave, ratio, f, fbeg, stepa, stepb, vquad_r, fbase_r, minf;
+    I ntrits, itest, nfsav, nresc, kopt, kbase, knew, nf, kpt, pc, rc, nrem_r;
+    I in_rescue_from_main;
+    I n_rescue;   // statistics only
+};
+typedef StateT<double, int> State;       // one patch, contiguous (host, shared-memory slots of the persistent kernel)
+typedef StateT<SD, SI> StateTile;        // lane view into a tile of BQ_TILE_LANES interleaved states (wavefront kernels)
+template <class ST> struct is_tile { static constexpr bool value = false; };
+template <> struct is_tile<StateTile> { static constexpr bool value = true; };
 
 // program counters (resume points)
 enum : int {
-    PC_PRELIM_EVAL = 1, PC_MAIN_EVAL = 2, PC_RESCUE_EVAL = 3, PC_FINISHED = 4, PC_YIELD_TRUST = 5
+    PC_PRELIM_EVAL = 1, PC_MAIN_EVAL = 2, PC_RESCUE_EVAL = 3, PC_FINISHED = 4, PC_YIELD_TRUST = 5,
+    PC_YIELD_LABEL = 16        // + label: advance() stopped in front of a heavy label its PHASES mask excludes (wavefront kernels)
 };
 
 // labels of the main iteration, numbered in flow order (the warp scheduler runs the smallest one present)
 enum : int {
     L_AFTER_EVAL = 0, L_RESCUE_LOOP = 1, L_RESCUE_DONE = 2, L_GOPT_FIX = 3, L_FARPOINT = 4, L_REDUCE_RHO = 5, L_TRUST = 6,
     L_SHIFT = 7, L_RESCUE = 8, L_ALTMOV = 9, L_VLAG = 10, L_EVAL = 11, L_EXIT = 12, L_NONE = 13
+};
+// The heavy label blocks.  advance<ST, PHASES> runs a heavy block only when its bit is set in PHASES and otherwise hands the patch
+// back (YIELD, S.pc = PC_YIELD_LABEL + label); the light blocks (bookkeeping between them) run in every phase.  The wavefront engine
+// launches one kernel per phase, so each kernel's instruction footprint is a fraction of the whole state machine.
+enum : unsigned {
+    PH_HEAVY = (1u << L_AFTER_EVAL) | (1u << L_RESCUE_LOOP) | (1u << L_TRUST) | (1u << L_SHIFT) | (1u << L_RESCUE) | (1u << L_ALTMOV) | (1u << L_VLAG),
+    PH_A = (1u << L_AFTER_EVAL) | (1u << L_RESCUE_LOOP) | (1u << L_RESCUE),     // entered with a fresh objective value
+    PH_T = (1u << L_TRUST),
+    PH_B = (1u << L_SHIFT) | (1u << L_ALTMOV) | (1u << L_VLAG),
+    PH_ALL = PH_A | PH_T | PH_B
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -156,11 +207,13 @@ BQ_HD double default_step(double lb, double ub, double x) {
 // ---------------------------------------------------------------------------------------------------------
 // H-matrix update when interpolation point `knew` moves (Powell's UPDATE)
 // ---------------------------------------------------------------------------------------------------------
-BQ_HDN void update(State& S, double beta, double denom, int knew, double* w) {
+template <class ST>
+BQ_HDN void update(ST& S, double beta, double denom, int knew, typename ST::real* w) {
+    typedef typename ST::real R;
     BQ_ASSUME_SHARED(S);
-    double (*zmat)[NPTM] = S.zmat;
-    double (*bmat)[N] = S.bmat;
-    double* vlag = S.vlag;
+    R (*zmat)[NPTM] = S.zmat;
+    R (*bmat)[N] = S.bmat;
+    R* vlag = S.vlag;
     double ztest = 0.0;
     BQ_NOUNROLL for (int k = 0; k < NPT; k++)
         BQ_UNROLL for (int j = 0; j < NPTM; j++) ztest = dmax(ztest, fabs(zmat[k][j]));
@@ -206,13 +259,15 @@ BQ_HDN void update(State& S, double beta, double denom, int knew, double* w) {
 // ALTMOV: alternative positions for interpolation point knew (line search through xopt + Cauchy step)
 // glag = w[0..2], hcol = w[3..9], wa = w[10..15]
 // ---------------------------------------------------------------------------------------------------------
-BQ_HDN void altmov(State& S) {
+template <class ST>
+BQ_HDN void altmov(ST& S) {
+    typedef typename ST::real R;
     BQ_ASSUME_SHARED(S);
-    double (*xpt)[N] = S.xpt;
-    double (*zmat)[NPTM] = S.zmat;
-    double (*bmat)[N] = S.bmat;
-    double* xopt = S.xopt; double* sl = S.sl; double* su = S.su; double* xnew = S.xnew; double* xalt = S.xalt;
-    double* glag = S.w; double* hcol = S.w + NP - 1; double* wa = S.w + NDIM;
+    R (*xpt)[N] = S.xpt;
+    R (*zmat)[NPTM] = S.zmat;
+    R (*bmat)[N] = S.bmat;
+    R* xopt = S.xopt; R* sl = S.sl; R* su = S.su; R* xnew = S.xnew; R* xalt = S.xalt;
+    R* glag = S.w; R* hcol = S.w + NP - 1; R* wa = S.w + NDIM;
     const int kopt = S.kopt, knew = S.knew;
     const double adelt = S.adelt;
     const double cnst = 1.0 + sqrt(2.0);
@@ -365,7 +420,8 @@ BQ_HDN void altmov(State& S) {
 // TRSBOX: truncated conjugate gradients inside the trust region with simple bounds, followed by the
 // boundary (two-dimensional) refinements.  gnew=w[0..2] xbdi=w[3..5] s=w[6..8] hs=w[9..11] hred=w[12..14]
 // ---------------------------------------------------------------------------------------------------------
-BQ_HD void hess_mul(const State& S, const double* s, double* hs) {
+template <class ST>
+BQ_HD void hess_mul(const ST& S, const double* s, double* hs) {
     BQ_ASSUME_SHARED(S);
     int ih = 0;
     BQ_UNROLL for (int j = 0; j < N; j++) {
@@ -386,7 +442,8 @@ BQ_HD void hess_mul(const State& S, const double* s, double* hs) {
     }
 }
 
-BQ_HDN void trsbox(State& S, unsigned wmask) {
+template <class ST>
+BQ_HDN void trsbox(ST& S, unsigned wmask) {
     BQ_ASSUME_SHARED(S);
     // All N-vectors of this routine live in registers (every loop over N below is fully unrolled so that the
     // indices are static); shared memory is only read (xpt, hq, pq) until the results are stored at T_FINISH.
@@ -644,7 +701,8 @@ BQ_HDN void trsbox(State& S, unsigned wmask) {
 }
 
 // point handed to the objective: x = clamp(xbase + p) with exact bounds where p sits on sl/su
-BQ_HD void point_from(State& S, const double* p) {
+template <class ST>
+BQ_HD void point_from(ST& S, const typename ST::real* p) {
     BQ_ASSUME_SHARED(S);
     BQ_NOUNROLL for (int i = 0; i < N; i++) {
         S.x[i] = dmin(dmax(S.xl[i], S.xbase[i] + p[i]), S.xu[i]);
@@ -657,12 +715,14 @@ BQ_HD void point_from(State& S, const double* p) {
 // RESCUE, part 1: rebuild bmat/zmat around xopt with provisional points (no objective evaluations yet).
 // ptsaux = w[0..5] (ptsaux[j][0|1] -> w[2j], w[2j+1]), ptsid = w[6..12], scratch wr = w[13..29]
 // ---------------------------------------------------------------------------------------------------------
-BQ_HDN void rescue_setup(State& S) {
+template <class ST>
+BQ_HDN void rescue_setup(ST& S) {
+    typedef typename ST::real R;
     BQ_ASSUME_SHARED(S);
-    double (*xpt)[N] = S.xpt; double (*bmat)[N] = S.bmat; double (*zmat)[NPTM] = S.zmat;
-    double* xopt = S.xopt; double* sl = S.sl; double* su = S.su; double* hq = S.hq; double* pq = S.pq;
-    double* vlag = S.vlag;
-    double* ptsaux = S.w; double* ptsid = S.w + 6; double* wr = S.w + 13;
+    R (*xpt)[N] = S.xpt; R (*bmat)[N] = S.bmat; R (*zmat)[NPTM] = S.zmat;
+    R* xopt = S.xopt; R* sl = S.sl; R* su = S.su; R* hq = S.hq; R* pq = S.pq;
+    R* vlag = S.vlag;
+    R* ptsaux = S.w; R* ptsid = S.w + 6; R* wr = S.w + 13;
     const double delta = S.delta;
     const double sfrac = 0.5 / (double)NP;
     double sumpq = 0.0, winc = 0.0;
@@ -801,11 +861,13 @@ BQ_HDN void rescue_setup(State& S) {
 }
 
 // RESCUE, part 2a: place provisional point kpt, predict the model there, emit the point to evaluate.
-BQ_HDN void rescue_place(State& S, int kpt) {
+template <class ST>
+BQ_HDN void rescue_place(ST& S, int kpt) {
+    typedef typename ST::real R;
     BQ_ASSUME_SHARED(S);
-    double (*xpt)[N] = S.xpt;
-    double* hq = S.hq; double* pq = S.pq; double* gopt = S.gopt;
-    double* ptsaux = S.w; double* ptsid = S.w + 6; double* wr = S.w + 13;
+    R (*xpt)[N] = S.xpt;
+    R* hq = S.hq; R* pq = S.pq; R* gopt = S.gopt;
+    R* ptsaux = S.w; R* ptsid = S.w + 6; R* wr = S.w + 13;
     int ih = 0;
     BQ_NOUNROLL for (int j = 0; j < N; j++) {
         wr[j] = xpt[kpt][j];
@@ -850,11 +912,13 @@ BQ_HDN void rescue_place(State& S, int kpt) {
 }
 
 // RESCUE, part 2b: absorb f at provisional point kpt into the model.
-BQ_HDN void rescue_absorb(State& S, int kpt, double f) {
+template <class ST>
+BQ_HDN void rescue_absorb(ST& S, int kpt, double f) {
+    typedef typename ST::real R;
     BQ_ASSUME_SHARED(S);
-    double (*bmat)[N] = S.bmat; double (*zmat)[NPTM] = S.zmat;
-    double* hq = S.hq; double* pq = S.pq; double* gopt = S.gopt;
-    double* ptsaux = S.w; double* ptsid = S.w + 6;
+    R (*bmat)[N] = S.bmat; R (*zmat)[NPTM] = S.zmat;
+    R* hq = S.hq; R* pq = S.pq; R* gopt = S.gopt;
+    R* ptsaux = S.w; R* ptsid = S.w + 6;
     const double diff = f - S.vquad_r;
     BQ_UNROLL for (int i = 0; i < N; i++) gopt[i] += diff * bmat[kpt][i];
     BQ_NOUNROLL for (int k = 0; k < NPT; k++) {
@@ -890,9 +954,9 @@ BQ_HDN void rescue_absorb(State& S, int kpt, double f) {
 // start: nlopt_optimize_ glue + bobyqa() preparation.  x0/lb/ub are in the caller's (unscaled) space.
 // Returns ASK with the first point in xs_out (unscaled), or DONE with S.rc set on invalid arguments.
 // ---------------------------------------------------------------------------------------------------------
-BQ_HDN int advance(State& S, double f_in, double* xs_out);
 
-BQ_HDN int start(State& S, const double* x0, const double* lb, const double* ub, double xtol_rel, int maxeval,
+template <class ST>
+BQ_HDN int start(ST& S, const double* x0, const double* lb, const double* ub, double xtol_rel, int maxeval,
                  double* xs_out) {
     BQ_ASSUME_SHARED(S);
     S.maxeval = maxeval;
@@ -956,16 +1020,19 @@ BQ_HDN int start(State& S, const double* x0, const double* lb, const double* ub,
 }
 
 // final point in the caller's space (bobyqb exit block + unscale)
-BQ_HD void result_x(const State& S, double* xs_out) {
+template <class ST>
+BQ_HD void result_x(const ST& S, double* xs_out) {
     BQ_UNROLL for (int i = 0; i < N; i++) xs_out[i] = S.x[i] * S.scl[i];
 }
 
-BQ_HDN int advance(State& S, double f_in, double* xs_out) {
+template <class ST, unsigned PHASES = PH_ALL, bool DEFER = true>
+BQ_HDN int advance(ST& S, double f_in, double* xs_out) {
+    typedef typename ST::real R;
     BQ_ASSUME_SHARED(S);
-    double (*xpt)[N] = S.xpt; double (*bmat)[N] = S.bmat; double (*zmat)[NPTM] = S.zmat;
-    double* xopt = S.xopt; double* gopt = S.gopt; double* hq = S.hq; double* pq = S.pq; double* fval = S.fval;
-    double* sl = S.sl; double* su = S.su; double* xnew = S.xnew; double* xalt = S.xalt; double* d = S.d;
-    double* vlag = S.vlag; double* w = S.w;
+    R (*xpt)[N] = S.xpt; R (*bmat)[N] = S.bmat; R (*zmat)[NPTM] = S.zmat;
+    R* xopt = S.xopt; R* gopt = S.gopt; R* hq = S.hq; R* pq = S.pq; R* fval = S.fval;
+    R* sl = S.sl; R* su = S.su; R* xnew = S.xnew; R* xalt = S.xalt; R* d = S.d;
+    R* vlag = S.vlag; R* w = S.w;
     int lbl = L_NONE;
     int result = DONE;
     bool done = false;
@@ -1054,6 +1121,9 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
     } else if (S.pc == PC_YIELD_TRUST) {
         S.pc = PC_MAIN_EVAL;
         lbl = L_TRUST;
+    } else if (S.pc >= PC_YIELD_LABEL) {
+        lbl = S.pc - PC_YIELD_LABEL;
+        S.pc = PC_MAIN_EVAL;
     } else if (S.pc == PC_MAIN_EVAL) {
         S.nevals++;
         S.f = f_in;
@@ -1078,6 +1148,10 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
     int ntrust = 0;   // trust-region steps taken in this call (BQ_DEFER_TRUST)
     (void)ntrust;
     for (;;) {
+        if (PHASES != PH_ALL && !done && lbl < 32 && ((PH_HEAVY >> lbl) & 1u) && !((PHASES >> lbl) & 1u)) {
+            S.pc = PC_YIELD_LABEL + lbl;      // this phase does not run the block: the kernel of its phase picks the patch up
+            result = YIELD; done = true;
+        }
         BQ_SCHED_BEGIN(wmask, done, lbl)
 #if defined(__CUDA_ARCH__)
         const unsigned sel = __activemask();
@@ -1114,7 +1188,7 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
         // -------------------------------------------------------------- trust-region step
         case L_TRUST: {
 #if defined(__CUDA_ARCH__) && BQ_DEFER_TRUST > 0
-            if (ntrust >= 1 && __popc(wmask) >= BQ_DEFER_TRUST) {
+            if (DEFER && ntrust >= 1 && __popc(wmask) >= BQ_DEFER_TRUST) {
                 S.pc = PC_YIELD_TRUST;
                 result = YIELD; done = true;
                 break;
@@ -1223,7 +1297,7 @@ BQ_HDN int advance(State& S, double f_in, double* xs_out) {
             break;
         }
         case L_RESCUE_LOOP: {
-            double* ptsid = S.w + 6;
+            R* ptsid = S.w + 6;
             int kpt = S.kpt;
             while (kpt < NPT && ptsid[kpt] == 0.0) kpt++;
             if (kpt >= NPT) { lbl = L_RESCUE_DONE; break; }

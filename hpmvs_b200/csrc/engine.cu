@@ -515,6 +515,24 @@ int hpmvs_optimize_batch_device(hpmvs_engine_t* e, int n, const hpmvs_patch_t* d
     return launch_optimize(e, n, d_in, d_out, stream ? (cudaStream_t)stream : e->stream);
 }
 
+int hpmvs_start_parameters(hpmvs_engine_t* e, int n, const hpmvs_patch_t* in, double* out) {
+    if (!e || n < 0 || (n > 0 && (!in || !out))) return HPMVS_E_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (e->ncams <= 0) return HPMVS_E_STATE;
+    host_start_parameters(e, n, in, out);
+    return 0;
+}
+
+int hpmvs_optimize_batch_device_start(hpmvs_engine_t* e, int n, const hpmvs_patch_t* d_in, hpmvs_patch_t* d_out, const double* d_start,
+                                      void* stream) {
+    if (!e || n < 0 || (n > 0 && (!d_in || !d_out))) return HPMVS_E_ARG;
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(e->mu);
+    HP_CUDA(cudaSetDevice(e->device));
+    e->next_start = d_start;
+    return launch_optimize(e, n, d_in, d_out, stream ? (cudaStream_t)stream : e->stream);
+}
+
 int hpmvs_engine_set_start_mode(hpmvs_engine_t* e, int mode) {
     if (!e || (mode != 0 && mode != 1)) return HPMVS_E_ARG;
     std::lock_guard<std::mutex> lk(e->mu);

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#include <algorithm>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -236,12 +237,94 @@ int hpmvs_pipeline_run(hpmvs_engine_t* e, const hpmvs_pipeline_params_t* params,
 
 void hpmvs_free(void* p) { std::free(p); }
 
+// Root cube of the patch octree as Scene::initPatches forms it (src/hpmvs/Scene.cpp:186-193, getBoundingBox :329-349): f32 bounding box
+// of the patch centres, edge = the largest extent, centred on the box.  origin = low corner.
+int hpmvs_root_cube(int n, const hpmvs_patch_t* patches, double origin[3], double* width) {
+    if (n <= 0 || !patches || !origin || !width) return HPMVS_E_ARG;
+    float mn[3], mx[3];
+    for (int a = 0; a < 3; a++) { mn[a] = patches[0].center[a]; mx[a] = patches[0].center[a]; }
+    for (int i = 1; i < n; i++)
+        for (int a = 0; a < 3; a++) { mn[a] = std::min(mn[a], patches[i].center[a]); mx[a] = std::max(mx[a], patches[i].center[a]); }
+    const float w = std::max(mx[0] - mn[0], std::max(mx[1] - mn[1], mx[2] - mn[2]));
+    for (int a = 0; a < 3; a++) origin[a] = (double)((mn[a] + mx[a]) / 2.0f) - (double)w / 2.0;
+    *width = (double)w;
+    return 0;
+}
+
+// Multi-GPU partition of a patch set by octree sub-tree, the reference's own split (getSubTrees, src/main.cpp:50-96, on top of
+// DynOctTree::getSubTrees, include/hpmvs/doctree.h:513-523): the root cube is split into its (non-empty) children, then the sub-tree
+// holding the most patches is split again until there are at least `min_subtrees` of them or the biggest holds fewer than 100
+// (main.cpp:74).  The sub-trees are dealt to `nranks` ranks greedily: biggest first, each to the least loaded rank (the reference
+// lets OpenMP's dynamic schedule do that, main.cpp:150).  cell_of[i] = sub-tree of patch i (-1: outside the root cube),
+// rank_of[i] = its rank (-1 likewise).  Returns the number of sub-trees.
+int hpmvs_shard_cells(int n, const hpmvs_patch_t* patches, const double origin[3], double root_width, int min_subtrees, int nranks,
+                      int32_t* cell_of, int32_t* rank_of) {
+    if (n < 0 || (n > 0 && (!patches || !cell_of || !rank_of)) || !origin || !(root_width > 0.0) || nranks < 1) return HPMVS_E_ARG;
+    const int MAXL = 20;
+    struct Sub { int level; uint32_t k[3]; std::vector<int> pts; };
+    std::vector<Sub> subs;
+    std::vector<uint32_t> q((size_t)n * 3);        // integer cell coordinates at level MAXL
+    Sub root; root.level = 0; root.k[0] = root.k[1] = root.k[2] = 0;
+    for (int i = 0; i < n; i++) {
+        cell_of[i] = -1; rank_of[i] = -1;
+        bool inside = true;
+        for (int a = 0; a < 3; a++) {
+            const double rel = ((double)patches[i].center[a] - origin[a]) / root_width;
+            // the box is closed at the top in the reference (a centre on the max face sits in the last cell)
+            if (!(rel >= 0.0 && rel <= 1.0)) { inside = false; break; }
+            const double c = std::floor(rel * (double)(1u << MAXL));
+            q[3 * (size_t)i + a] = (uint32_t)std::min(c, (double)((1u << MAXL) - 1));
+        }
+        if (inside) root.pts.push_back(i);
+    }
+    auto split = [&](const Sub& s, std::vector<Sub>& out) {
+        Sub ch[8];
+        const int sh = MAXL - (s.level + 1);
+        for (int c = 0; c < 8; c++) {
+            ch[c].level = s.level + 1;
+            for (int a = 0; a < 3; a++) ch[c].k[a] = (s.k[a] << 1) | ((c >> a) & 1);
+        }
+        for (int i : s.pts) {
+            int c = 0;
+            for (int a = 0; a < 3; a++) c |= (int)((q[3 * (size_t)i + a] >> sh) & 1u) << a;
+            ch[c].pts.push_back(i);
+        }
+        for (int c = 0; c < 8; c++) if (!ch[c].pts.empty()) out.push_back(std::move(ch[c]));
+    };
+    if (min_subtrees < 2) subs.push_back(std::move(root));
+    else {
+        split(root, subs);
+        while ((int)subs.size() < min_subtrees && !subs.empty()) {
+            size_t big = 0;
+            for (size_t i = 1; i < subs.size(); i++) if (subs[i].pts.size() > subs[big].pts.size()) big = i;
+            if (subs[big].pts.size() < 100 || subs[big].level >= MAXL) break;
+            std::vector<Sub> next;
+            split(subs[big], next);
+            for (size_t i = 0; i < subs.size(); i++) if (i != big) next.push_back(std::move(subs[i]));
+            subs.swap(next);
+        }
+    }
+    std::vector<int> order(subs.size());
+    for (size_t i = 0; i < subs.size(); i++) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return subs[a].pts.size() > subs[b].pts.size(); });
+    std::vector<int64_t> load((size_t)nranks, 0);
+    for (int si : order) {
+        int r = 0;
+        for (int j = 1; j < nranks; j++) if (load[j] < load[r]) r = j;
+        load[r] += (int64_t)subs[si].pts.size();
+        for (int i : subs[si].pts) { cell_of[i] = si; rank_of[i] = r; }
+    }
+    return (int)subs.size();
+}
+
 // Border de-duplication after the final multi-GPU gather: patches of DIFFERENT ranks that fall into the same cubic cell of edge `cell`
 // are reduced to the best-supported one - most views first (CellProcessor::filter, src/hpmvs/CellProcessor.cpp:43-82), then the lower
 // final score, then the lower rank; patches of the winner's own rank in that cell all stay (merging inside a shard is the scheduler's
 // job).  keep[] receives the surviving indices in ascending order; returns their number.
-int hpmvs_dedup_border(int n, const hpmvs_patch_t* rec, const int32_t* owner, double cell, int32_t* keep) {
+int hpmvs_dedup_border(int n, const hpmvs_patch_t* rec, const int32_t* owner, const double origin[3], double cell, int32_t* keep) {
     if (n < 0 || (n > 0 && (!rec || !owner || !keep)) || !(cell > 0.0)) return HPMVS_E_ARG;
+    const double zero[3] = {0.0, 0.0, 0.0};
+    if (!origin) origin = zero;
     struct Best { int idx; };
     struct Key { int64_t k[3]; bool operator==(const Key& o) const { return k[0] == o.k[0] && k[1] == o.k[1] && k[2] == o.k[2]; } };
     struct KeyHash { size_t operator()(const Key& a) const { return (size_t)(a.k[0] * 73856093ll ^ a.k[1] * 19349663ll ^ a.k[2] * 83492791ll); } };
@@ -255,7 +338,7 @@ int hpmvs_dedup_border(int n, const hpmvs_patch_t* rec, const int32_t* owner, do
     };
     for (int i = 0; i < n; i++) {
         if (rec[i].status != HPMVS_OK) continue;
-        for (int a = 0; a < 3; a++) keys[i].k[a] = (int64_t)std::floor((double)rec[i].center[a] / cell);
+        for (int a = 0; a < 3; a++) keys[i].k[a] = (int64_t)std::floor(((double)rec[i].center[a] - origin[a]) / cell);
         auto it = best.find(keys[i]);
         if (it == best.end()) best[keys[i]] = i;
         else if (better(i, it->second)) it->second = i;

@@ -707,7 +707,9 @@ __device__ __forceinline__ void init_parameters(LaneCtx& P, const KParams& K, co
     x[1] /= (double)K.angle_scale;
     x[2] /= (double)K.angle_scale;
     for (int i = 0; i < 3; i++) x[i] = fmin(ub[i], fmax(lb[i], x[i]));
-    if (K.start) { x[1] = K.start[2 * P.patch_index]; x[2] = K.start[2 * P.patch_index + 1]; }
+    // host-evaluated angles were formed with the camera axes of the INPUT reference view; sortImages (:183-223) drops views with
+    // cosa <= 0, so the reference view can change - then the device values above stand (the host cannot know the new view)
+    if (K.start && (int)P.images[0] == K.in[P.patch_index].images[0]) { x[1] = K.start[2 * P.patch_index]; x[2] = K.start[2 * P.patch_index + 1]; }
 }
 
 // Scene::getColor(const Patch3d&) (Scene.cpp:300-327): lane = view; stable rank by colour norm

@@ -69,6 +69,8 @@ def _lib():
         L.hpmvs_engine_set_covis.argtypes = [vp, ip, ip]
         L.hpmvs_optimize_batch.argtypes = [vp, C.c_int, vp, vp, vp]
         L.hpmvs_optimize_batch_device.argtypes = [vp, C.c_int, vp, vp, vp]
+        L.hpmvs_start_parameters.argtypes = [vp, C.c_int, vp, dp]
+        L.hpmvs_optimize_batch_device_start.argtypes = [vp, C.c_int, vp, vp, vp, vp]
         L.hpmvs_ncc_batch.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, fp, vp]
         L.hpmvs_ncc_batch_device.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, vp]
         L.hpmvs_engine_set_start_mode.argtypes = [vp, C.c_int]
@@ -235,6 +237,17 @@ class Engine:
     def optimize_device(self, n: int, d_in: int, d_out: int, stream: int = 0) -> None:
         """Device-resident records, asynchronous on `stream` (0 = the engine's stream)."""
         _check(_lib().hpmvs_optimize_batch_device(self._h, n, d_in, d_out, stream or None))
+
+    def start_parameters(self, patches: np.ndarray) -> np.ndarray:
+        """parametersFromCenterNorm's two start angles per record with THIS machine's libm (start mode 1) -> [n, 2] f64."""
+        assert patches.dtype == PATCH_DTYPE and patches.flags.c_contiguous
+        out = np.zeros((len(patches), 2), np.float64)
+        _check(_lib().hpmvs_start_parameters(self._h, len(patches), patches.ctypes.data, _p(out, C.c_double)))
+        return out
+
+    def optimize_device_start(self, n: int, d_in: int, d_out: int, d_start: int, stream: int = 0) -> None:
+        """Device-resident records + device-resident start angles (start mode 1), asynchronous on `stream`."""
+        _check(_lib().hpmvs_optimize_batch_device_start(self._h, n, d_in, d_out, d_start or None, stream or None))
 
     def ncc(self, patches: np.ndarray, ref_idx: int = 0, robust: bool = False) -> np.ndarray:
         """n x PatchOptimizer::setINCCs (PatchOptimizer.cpp:448-474) -> [n, MAX_VIEWS] f32."""

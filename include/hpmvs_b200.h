@@ -151,6 +151,13 @@ int  hpmvs_engine_set_start_mode(hpmvs_engine_t *e, int mode);
 int  hpmvs_optimize_batch_device(hpmvs_engine_t *e, int n, const hpmvs_patch_t *d_in, hpmvs_patch_t *d_out,
                                  void *stream);
 
+/* Start mode 1 for device-resident records: hpmvs_start_parameters() evaluates parametersFromCenterNorm's two angles
+ * (PatchOptimizer.cpp:427-443) for n HOST records with the caller's libm into out[2*n] (host); the caller copies them to the device
+ * next to the records and passes them as d_start (NULL = mode 0). */
+int  hpmvs_start_parameters(hpmvs_engine_t *e, int n, const hpmvs_patch_t *in, double *out);
+int  hpmvs_optimize_batch_device_start(hpmvs_engine_t *e, int n, const hpmvs_patch_t *d_in, hpmvs_patch_t *d_out,
+                                       const double *d_start, void *stream);
+
 /* Replaces n calls of PatchOptimizer::setINCCs (PatchOptimizer.cpp:448-474) on patches as given:
  * inccs[i*HPMVS_MAX_VIEWS + k] = (robust ? r/(1+3r) : r), r = 1-NCC(view ref_idx, view k); 2.0 where invalid. */
 int  hpmvs_ncc_batch(hpmvs_engine_t *e, int n, const hpmvs_patch_t *in, int ref_idx, int robust, float *inccs,
@@ -210,9 +217,19 @@ int  hpmvs_pipeline_run(hpmvs_engine_t *e, const hpmvs_pipeline_params_t *params
 void hpmvs_free(void *p);
 /* Border de-duplication after the final multi-GPU gather of the patch records (host C++; the gather itself is an NCCL all_gather,
  * hpmvs_b200/gather.py): patches of different ranks (owner[i]) in the same cubic cell of edge `cell` are reduced to the best-supported
- * one (most views, CellProcessor::filter, CellProcessor.cpp:43-82; then lower score, then lower rank); keep[] receives the surviving
+ * one (most views, CellProcessor::filter, CellProcessor.cpp:43-82; then lower score, then lower rank); cells are counted from `origin`
+ * (the octree's low corner; NULL = world origin); keep[] receives the surviving
  * indices in ascending order (capacity n), the return value is their number. */
-int  hpmvs_dedup_border(int n, const hpmvs_patch_t *records, const int32_t *owner, double cell, int32_t *keep);
+int  hpmvs_dedup_border(int n, const hpmvs_patch_t *records, const int32_t *owner, const double origin[3], double cell, int32_t *keep);
+/* Root cube of the patch octree as Scene::initPatches forms it (src/hpmvs/Scene.cpp:186-193): f32 bounding box of the centres, edge =
+ * largest extent, centred on the box; origin = its low corner. */
+int  hpmvs_root_cube(int n, const hpmvs_patch_t *patches, double origin[3], double *width);
+/* Replaces getSubTrees (src/main.cpp:50-96; DynOctTree::getSubTrees, include/hpmvs/doctree.h:513-523) as a partition of a patch set:
+ * split the root cube into its non-empty children, keep splitting the sub-tree with the most patches until there are >= min_subtrees
+ * (or the biggest holds < 100, main.cpp:74); deal the sub-trees to nranks ranks, biggest first to the least loaded rank.
+ * cell_of[i] / rank_of[i] = sub-tree / rank of patch i (-1 outside the cube).  Returns the number of sub-trees. */
+int  hpmvs_shard_cells(int n, const hpmvs_patch_t *patches, const double origin[3], double root_width, int min_subtrees, int nranks,
+                       int32_t *cell_of, int32_t *rank_of);
 
 /* ---- host-side scene surface (plain C++ on the host, no GPU needed): what feeds the engine ---- */
 

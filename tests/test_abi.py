@@ -78,13 +78,13 @@ def test_nvm_round_trip(tmp_path):
 def test_host_entry_points_reject_bad_arguments():
     # no GPU needed: the host-side entry points validate before they touch a device
     lib = C.CDLL(_native.build())
-    lib.hpmvs_dedup_border.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    lib.hpmvs_dedup_border.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
     lib.hpmvs_undistort_rgb.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
     lib.hpmvs_pipeline_run.argtypes = [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 4
-    assert lib.hpmvs_dedup_border(-1, None, None, 1.0, None) < 0
-    assert lib.hpmvs_dedup_border(3, None, None, 1.0, None) < 0
-    assert lib.hpmvs_dedup_border(0, None, None, 0.0, None) < 0          # cell edge must be positive
-    assert lib.hpmvs_dedup_border(0, None, None, 1.0, None) == 0         # empty input is fine
+    assert lib.hpmvs_dedup_border(-1, None, None, None, 1.0, None) < 0
+    assert lib.hpmvs_dedup_border(3, None, None, None, 1.0, None) < 0
+    assert lib.hpmvs_dedup_border(0, None, None, None, 0.0, None) < 0          # cell edge must be positive
+    assert lib.hpmvs_dedup_border(0, None, None, None, 1.0, None) == 0         # empty input is fine
     assert lib.hpmvs_undistort_rgb(None, 4, 4, 100.0, 0.1, None, None) < 0
     img = np.zeros((4, 4, 3), np.uint8)
     assert lib.hpmvs_undistort_rgb(img.ctypes.data, 0, 4, 100.0, 0.1, img.ctypes.data, None) < 0

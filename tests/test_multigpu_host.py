@@ -39,6 +39,79 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _worker_root(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(7)                       # the same batch on every rank, sharded by octree sub-tree
+    allp = _make(900, 0, rng)
+    origin, width = gather.root_cube(allp)
+    cell, rk, ncell = gather.shard_cells(allp, origin, width, 16, world)
+    mine = np.ascontiguousarray(allp[rk == rank])
+    got, owner = gather.gather_to_root(mine)
+    e, _ = gather.gather_to_root(np.zeros(0, hp.PATCH_DTYPE))
+    if rank == 0:
+        q.put((rank, got.tobytes(), owner.tolist(), len(e), rk.tolist()))
+    else:
+        q.put((rank, b"" if got is None else b"x", [] if owner is None else [1], -1 if e is None else len(e), rk.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_unpadded_gather_to_root_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_worker_root, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps: p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in ps: p.join(60)
+    assert all(p.exitcode == 0 for p in ps)
+    (r0, b0, o0, e0, rk0), (r1, b1, o1, e1, rk1) = res
+    assert rk0 == rk1                                          # every rank computes the same partition
+    assert b1 == b"" and o1 == [] and e1 == -1 and e0 == 0     # only the root receives
+    allp = _make(900, 0, np.random.default_rng(7))
+    rk = np.asarray(rk0)
+    want = np.concatenate([allp[rk == 0], allp[rk == 1]])
+    assert b0 == want.tobytes() and o0 == [0] * int((rk == 0).sum()) + [1] * int((rk == 1).sum())
+
+
+def test_shard_cells_is_the_reference_subtree_split():
+    """hpmvs_shard_cells against a plain restatement of getSubTrees (src/main.cpp:50-96): split the root into its non-empty children,
+    keep splitting the fullest sub-tree until there are enough; every patch in exactly one sub-tree; ranks balanced greedily."""
+    rng = np.random.default_rng(3)
+    p = _make(5000, 0, rng)
+    p["center"][:2500, :3] *= 0.2                          # a dense clump: forces deep splits in one corner
+    origin, width = gather.root_cube(p)
+    c32 = p["center"][:, :3]
+    assert np.isclose(width, float((c32.max(0) - c32.min(0)).max())) and np.allclose(origin + width / 2, (c32.max(0) + c32.min(0)) / 2, atol=1e-6)
+    for want_trees, world in ((2, 1), (8, 2), (100, 4), (100, 8), (1, 3)):
+        cell, rk, ncell = gather.shard_cells(p, origin, width, want_trees, world)
+        assert (cell >= 0).all() and (rk >= 0).all() and rk.max() < world and cell.max() == ncell - 1
+        # restatement: cells as (level, ix, iy, iz) with point lists
+        rel = (p["center"][:, :3].astype(np.float64) - origin) / width
+        q = np.minimum(np.floor(rel * (1 << 20)), (1 << 20) - 1).astype(np.int64)
+        def split(level, idx):
+            sh = 20 - (level + 1)
+            code = ((q[idx, 0] >> sh) & 1) | (((q[idx, 1] >> sh) & 1) << 1) | (((q[idx, 2] >> sh) & 1) << 2)
+            return [(level + 1, idx[code == c]) for c in range(8) if (code == c).any()]
+        subs = [(0, np.arange(len(p)))] if want_trees < 2 else split(0, np.arange(len(p)))
+        while want_trees >= 2 and len(subs) < want_trees:
+            big = max(range(len(subs)), key=lambda i: (len(subs[i][1]), -i))
+            if len(subs[big][1]) < 100:
+                break
+            subs = split(*subs[big]) + [s for i, s in enumerate(subs) if i != big]
+        assert ncell == len(subs)
+        for i, (_, idx) in enumerate(subs):
+            assert (cell[idx] == i).all()
+            assert len(set(rk[idx].tolist())) == 1           # a sub-tree is never split over ranks
+        load = np.bincount(rk, minlength=world)
+        assert load.max() - load.min() <= max(len(s[1]) for s in subs)     # greedy biggest-first bound
+    # a patch outside the cube belongs to nobody
+    far = p[:3].copy(); far["center"][0, 0] = 1e3
+    cell, rk, _ = gather.shard_cells(far, origin, width, 8, 2)
+    assert cell[0] == -1 and rk[0] == -1 and (cell[1:] >= 0).all()
+
+
 def test_gather_and_dedup_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -83,5 +156,7 @@ def test_bench_shards_are_disjoint_and_deterministic():
     a, _ = bench.workload_scene("tiny", 0)
     b, _ = bench.workload_scene("tiny", 1)
     a2, _ = bench.workload_scene("tiny", 0)
+    # both arms print the same `config` object (the driver compares them)
+    assert bench.bench_config("city100", "d", 44000, 100, 4) == bench.bench_config("city100", "d", 44000, 100, 4)
     assert np.array_equal(a.points, a2.points) and not np.array_equal(a.points, b.points)
     assert all(np.array_equal(x, y) for x, y in zip(a.images, b.images))   # the scene is replicated, seeds are sharded
