@@ -14,7 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HPMVS_LIB") or os.path.join(_HERE, "libhpmvs_b200.so")   # HPMVS_LIB: A/B experiments only
 SOURCES = [os.path.join(_HERE, "csrc", "engine.cu"), os.path.join(_HERE, "csrc", "host_scene.cpp"),
            os.path.join(_HERE, "csrc", "host_io.cpp"), os.path.join(_HERE, "csrc", "host_pipeline.cpp")]
-HEADERS = [os.path.join(_HERE, "csrc", "patch_kernels.cuh"), os.path.join(_HERE, "csrc", "bobyqa3.h"),
+HEADERS = [os.path.join(_HERE, "csrc", "patch_kernels.cuh"), os.path.join(_HERE, "csrc", "patch_kernels_wf.cuh"),
+           os.path.join(_HERE, "csrc", "bobyqa3.h"), os.path.join(_HERE, "csrc", "undistort_math.h"),
            os.path.join(_HERE, "..", "include", "hpmvs_b200.h")]
 
 # -fmad=false / -ffp-contract=off: the kernels restate the reference's f32/f64 evaluation order (see

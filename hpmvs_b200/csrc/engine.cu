@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "patch_kernels.cuh"
+#include "patch_kernels_wf.cuh"
 
 #define HP_CUDA(call)                                                                                   \
     do {                                                                                                \
@@ -47,7 +48,10 @@ inline void h_normalized3(const float* a, float* o) {
 
 }  // namespace
 
-enum { HP_RING = 4 };
+enum { HP_RING = 4, HP_WF_PARTS = 8 };
+#ifndef HP_WF_DEFAULT_MODE
+#define HP_WF_DEFAULT_MODE 0
+#endif
 
 struct hpmvs_engine {
     int device = 0;
@@ -100,6 +104,32 @@ struct hpmvs_engine {
     int pool_ctas2[2] = {0, 0};
     cudaEvent_t pool_done[2] = {nullptr, nullptr};
     unsigned long long parked_seq = 0;
+    // wavefront form of the fused path (patch_kernels_wf.cuh): 0 = persistent kernels, 1 = per-phase kernels in a CUDA-graph WHILE loop,
+    // 2 = the same kernels launched round by round from the host (debugging; the call blocks)
+    int wf_mode = 0;
+    int wf_split = 1;                // 1: advance phases A / T / B as three kernels, 0: one kernel with every phase
+    int wf_capacity = 0;             // slots in flight per wavefront context
+    struct WfContext {
+        int capacity = 0;
+        hp::LaneCtx* ctx = nullptr; unsigned char* tiles = nullptr; double* fval = nullptr; int* sstate = nullptr;
+        int* eval_list = nullptr; int* post_list = nullptr; hp::WfCtl* ctl = nullptr;
+        hp::WfParams* d_params = nullptr;
+        hp::WfParams* h_params[2] = {nullptr, nullptr};      // pinned ring; a slot is rewritten only after the launch that used it finished
+        cudaEvent_t h_params_free[2] = {nullptr, nullptr};
+        hp::WfCtl* h_ctl = nullptr;                           // pinned: the control block of the last finished launch (overrun check)
+        unsigned long long seq = 0;
+        unsigned long long* round_log = nullptr;              // HPMVS_WF_LOG: per-round {ns, evals, posts, dead} of the last launch
+        cudaGraphConditionalHandle cond = 0;
+    };
+    // one launch = one CUDA graph with up to HP_WF_PARTS independent branches (fill kernel -> WHILE loop), one per sub-batch
+    struct WfBatch {
+        WfContext part[HP_WF_PARTS];
+        cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+        cudaEvent_t done = nullptr;
+    } wfb[2];
+    int wf_parts = 4;                // a batch is cut into up to this many sub-batches: their round loops interleave on the GPU
+    unsigned long long wf_seq = 0;
+    unsigned long long wf_overruns = 0;
     std::mutex mu;
 };
 
@@ -245,6 +275,17 @@ int hpmvs_engine_create(const hpmvs_options_t* opt, int device, hpmvs_engine_t**
                 if (g_pvariants[i].ow == ow && g_pvariants[i].sw == sw && g_pvariants[i].lpw == lpw) e->pvariant = (int)i;
     }
     HP_CUDA(cudaFuncSetAttribute(g_pvariants[e->pvariant].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_pvariants[e->pvariant].smem));
+    e->wf_mode = HP_WF_DEFAULT_MODE;
+    if (const char* wf = getenv("HPMVS_WF")) e->wf_mode = atoi(wf);
+    if (const char* ws = getenv("HPMVS_WF_SPLIT")) e->wf_split = atoi(ws);
+    e->wf_capacity = e->sm_count * 12 * 32;                                 // one full wave of advance threads (12 warps per SM)
+    if (const char* wp = getenv("HPMVS_WF_PARTS")) e->wf_parts = atoi(wp);
+    if (e->wf_parts < 1) e->wf_parts = 1;
+    if (e->wf_parts > HP_WF_PARTS) e->wf_parts = HP_WF_PARTS;
+    e->wf_capacity = e->wf_capacity / e->wf_parts;
+    if (const char* wc = getenv("HPMVS_WF_SLOTS")) e->wf_capacity = atoi(wc);
+    e->wf_capacity = (e->wf_capacity + hp::WF_ADV_THREADS - 1) / hp::WF_ADV_THREADS * hp::WF_ADV_THREADS;
+    if (e->wf_capacity < hp::WF_ADV_THREADS) e->wf_capacity = hp::WF_ADV_THREADS;
     *out = e;
     return 0;
 }
@@ -271,6 +312,17 @@ void hpmvs_engine_destroy(hpmvs_engine_t* e) {
     cudaFree(e->d_work); cudaFree(e->d_counters);
     for (int i = 0; i < HP_RING; i++) if (e->slot_done[i]) cudaEventDestroy(e->slot_done[i]);
     for (int i = 0; i < 2; i++) { cudaFree(e->d_pool_bq2[i]); cudaFree(e->d_pool_ctx2[i]); }
+    for (auto& b : e->wfb) {
+        if (b.done) { cudaEventSynchronize(b.done); cudaEventDestroy(b.done); }
+        if (b.exec) cudaGraphExecDestroy(b.exec);
+        if (b.graph) cudaGraphDestroy(b.graph);
+        for (auto& w : b.part) {
+            cudaFree(w.ctx); cudaFree(w.tiles); cudaFree(w.fval); cudaFree(w.sstate); cudaFree(w.eval_list); cudaFree(w.post_list);
+            cudaFree(w.ctl); cudaFree(w.d_params); cudaFree(w.round_log);
+            for (int i = 0; i < 2; i++) { if (w.h_params[i]) cudaFreeHost(w.h_params[i]); if (w.h_params_free[i]) cudaEventDestroy(w.h_params_free[i]); }
+            if (w.h_ctl) cudaFreeHost(w.h_ctl);
+        }
+    }
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
     cudaStreamDestroy(e->stream);
     delete e;
@@ -349,6 +401,33 @@ int hpmvs_engine_upload_image(hpmvs_engine_t* e, int cam, int level, const uint8
     HP_CUDA(cudaGetLastError());
     HP_CUDA(cudaStreamSynchronize(e->stream));
     if (e->h_cams[cam].w[level] != w || e->h_cams[cam].h[level] != h) return HPMVS_E_ARG;
+    return 0;
+}
+
+// Image::load's undistortion step (Image.cpp:51-53) on the device: uploads the DISTORTED level-0 image and writes the undistorted one
+// as level 0 of view `cam`; r == 0 is a plain upload.
+int hpmvs_engine_upload_image_undistort(hpmvs_engine_t* e, int cam, const uint8_t* rgb, int w, int h, size_t pitch_bytes, double f, double r) {
+    if ((float)r == 0.0f) return hpmvs_engine_upload_image(e, cam, 0, rgb, w, h, pitch_bytes);
+    if (!e || !rgb || cam < 0 || cam >= e->ncams || w <= 0 || h <= 0 || pitch_bytes < (size_t)3 * w) return HPMVS_E_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    HP_CUDA(cudaSetDevice(e->device));
+    int rc = ensure_level(e, cam, 0, w, h);
+    if (rc) return rc;
+    const size_t need = (size_t)3 * w * h;
+    if (need > e->cap_stage) {
+        if (e->d_stage) cudaFree(e->d_stage);
+        e->d_stage = nullptr; e->cap_stage = 0;
+        HP_CUDA(cudaMalloc(&e->d_stage, need));
+        e->cap_stage = need;
+    }
+    HP_CUDA(cudaMemcpy2DAsync(e->d_stage, (size_t)3 * w, rgb, pitch_bytes, (size_t)3 * w, h, cudaMemcpyHostToDevice, e->stream));
+    const LevelImage& li = e->images[cam][0];
+    dim3 blk(32, 8), grd((w + 31) / 32, (h + 7) / 8);
+    hp::undistort_kernel<<<grd, blk, 0, e->stream>>>(e->d_stage, w, h, (float)f, (float)r, li.data, li.pitch);
+    e->launches++;
+    HP_CUDA(cudaGetLastError());
+    HP_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->h_cams[cam].w[0] != w || e->h_cams[cam].h[0] != h) return HPMVS_E_ARG;
     return 0;
 }
 
@@ -444,11 +523,176 @@ static void host_start_parameters(hpmvs_engine* e, int n, const hpmvs_patch_t* i
     }
 }
 
+// ---- wavefront form: per-phase kernels in a CUDA-graph WHILE loop (patch_kernels_wf.cuh) ---------------------------------------------
+static int wf_ensure_context(hpmvs_engine* e, hpmvs_engine::WfContext& w) {
+    if (w.capacity) return 0;
+    const size_t cap = (size_t)e->wf_capacity;
+    HP_CUDA(cudaMalloc(&w.ctx, cap * sizeof(hp::LaneCtx)));
+    HP_CUDA(cudaMalloc(&w.tiles, cap / 32 * sizeof(bq3::StateTile)));
+    HP_CUDA(cudaMalloc(&w.fval, cap * sizeof(double)));
+    HP_CUDA(cudaMalloc(&w.sstate, cap * sizeof(int)));
+    HP_CUDA(cudaMalloc(&w.eval_list, cap * sizeof(int)));
+    HP_CUDA(cudaMalloc(&w.post_list, cap * sizeof(int)));
+    HP_CUDA(cudaMalloc(&w.ctl, sizeof(hp::WfCtl)));
+    HP_CUDA(cudaMalloc(&w.d_params, sizeof(hp::WfParams)));
+    for (int i = 0; i < 2; i++) {
+        HP_CUDA(cudaMallocHost(&w.h_params[i], sizeof(hp::WfParams)));
+        HP_CUDA(cudaEventCreateWithFlags(&w.h_params_free[i], cudaEventDisableTiming));
+    }
+    HP_CUDA(cudaMallocHost(&w.h_ctl, sizeof(hp::WfCtl)));
+    memset(w.h_ctl, 0, sizeof(hp::WfCtl));
+    if (getenv("HPMVS_WF_LOG")) HP_CUDA(cudaMalloc(&w.round_log, sizeof(unsigned long long) * 4 * 65536));
+    w.capacity = (int)cap;
+    return 0;
+}
+
+struct WfLaunchShape { dim3 grid_s, grid_a; size_t smem_s; };
+static WfLaunchShape wf_shape(const hpmvs_engine* e, const hpmvs_engine::WfContext& w) {
+    WfLaunchShape sh;
+    sh.smem_s = sizeof(hp::NccWarp) * hp::WF_SAMPLER_WARPS;
+    int per_sm = 7 / e->wf_parts;                                      // 7 CTAs x 4 warps x 7 KB per SM, shared by the sub-batches in flight
+    if (per_sm < 2) per_sm = 2;
+    sh.grid_s = dim3((unsigned)(e->sm_count * per_sm));
+    sh.grid_a = dim3((unsigned)(w.capacity / hp::WF_ADV_THREADS));
+    return sh;
+}
+
+// one round of the loop, enqueued on `s` (host-loop mode) - the graph body holds the same nodes in the same order
+static void wf_enqueue_round(const hpmvs_engine* e, const hpmvs_engine::WfContext& w, cudaStream_t s) {
+    const WfLaunchShape sh = wf_shape(e, w);
+    if (e->wf_split) {
+        hp::wf_advance_kernel<bq3::PH_A><<<sh.grid_a, hp::WF_ADV_THREADS, 0, s>>>(w.d_params);
+        hp::wf_advance_kernel<bq3::PH_T><<<sh.grid_a, hp::WF_ADV_THREADS, 0, s>>>(w.d_params);
+        hp::wf_advance_kernel<bq3::PH_B><<<sh.grid_a, hp::WF_ADV_THREADS, 0, s>>>(w.d_params);
+    } else {
+        hp::wf_advance_kernel<bq3::PH_ALL><<<sh.grid_a, hp::WF_ADV_THREADS, 0, s>>>(w.d_params);
+    }
+    hp::wf_eval_kernel<<<sh.grid_s, hp::WF_SAMPLER_WARPS * 32, sh.smem_s, s>>>(w.d_params);
+    hp::wf_post_kernel<false><<<sh.grid_s, hp::WF_SAMPLER_WARPS * 32, sh.smem_s, s>>>(w.d_params);
+    hp::wf_sched_kernel<<<1, 1, 0, s>>>(w.d_params);
+}
+
+static int wf_build_graph(hpmvs_engine* e, hpmvs_engine::WfBatch& b) {
+    if (b.exec) return 0;
+    HP_CUDA(cudaGraphCreate(&b.graph, 0));
+    for (int k = 0; k < e->wf_parts; k++) {
+        hpmvs_engine::WfContext& w = b.part[k];
+        const WfLaunchShape sh = wf_shape(e, w);
+        void* args[1] = {(void*)&w.d_params};
+        auto knode = [&](cudaGraph_t g, cudaGraphNode_t* node, const cudaGraphNode_t* dep, void* fn, dim3 grid, unsigned block, size_t smem) {
+            cudaKernelNodeParams kp{};
+            kp.func = fn; kp.gridDim = grid; kp.blockDim = dim3(block); kp.sharedMemBytes = (unsigned)smem; kp.kernelParams = args; kp.extra = nullptr;
+            return cudaGraphAddKernelNode(node, g, dep, dep ? 1 : 0, &kp);
+        };
+        cudaGraphNode_t fill, loop;
+        HP_CUDA(knode(b.graph, &fill, nullptr, (void*)hp::wf_post_kernel<true>, sh.grid_s, hp::WF_SAMPLER_WARPS * 32, sh.smem_s));
+        HP_CUDA(cudaGraphConditionalHandleCreate(&w.cond, b.graph, 1, cudaGraphCondAssignDefault));
+        cudaGraphNodeParams cp{};
+        cp.type = cudaGraphNodeTypeConditional;
+        cp.conditional.handle = w.cond;
+        cp.conditional.type = cudaGraphCondTypeWhile;
+        cp.conditional.size = 1;
+        HP_CUDA(cudaGraphAddNode(&loop, b.graph, &fill, 1, &cp));
+        cudaGraph_t body = cp.conditional.phGraph_out[0];
+        cudaGraphNode_t prev, node;
+        bool first = true;
+        auto chain = [&](void* fn, dim3 grid, unsigned block, size_t smem) {
+            const cudaError_t err = knode(body, &node, first ? nullptr : &prev, fn, grid, block, smem);
+            prev = node; first = false;
+            return err;
+        };
+        if (e->wf_split) {
+            HP_CUDA(chain((void*)hp::wf_advance_kernel<bq3::PH_A>, sh.grid_a, hp::WF_ADV_THREADS, 0));
+            HP_CUDA(chain((void*)hp::wf_advance_kernel<bq3::PH_T>, sh.grid_a, hp::WF_ADV_THREADS, 0));
+            HP_CUDA(chain((void*)hp::wf_advance_kernel<bq3::PH_B>, sh.grid_a, hp::WF_ADV_THREADS, 0));
+        } else {
+            HP_CUDA(chain((void*)hp::wf_advance_kernel<bq3::PH_ALL>, sh.grid_a, hp::WF_ADV_THREADS, 0));
+        }
+        HP_CUDA(chain((void*)hp::wf_eval_kernel, sh.grid_s, hp::WF_SAMPLER_WARPS * 32, sh.smem_s));
+        HP_CUDA(chain((void*)hp::wf_post_kernel<false>, sh.grid_s, hp::WF_SAMPLER_WARPS * 32, sh.smem_s));
+        HP_CUDA(chain((void*)hp::wf_sched_kernel, dim3(1), 1, 0));
+    }
+    HP_CUDA(cudaGraphInstantiate(&b.exec, b.graph, 0));
+    return 0;
+}
+
+// parameters + control block of one sub-batch, enqueued on `s` ahead of the graph launch
+static int wf_prepare_part(hpmvs_engine* e, hpmvs_engine::WfContext& w, int n, const hpmvs_patch_t* d_in, hpmvs_patch_t* d_out,
+                           const double* d_start, cudaStream_t s) {
+    const int ring = (int)(w.seq++ % 2);
+    HP_CUDA(cudaEventSynchronize(w.h_params_free[ring]));           // the launch that read this pinned block has finished
+    if (w.h_ctl->overrun) { e->wf_overruns++; w.h_ctl->overrun = 0; }
+    hp::WfParams& P = *w.h_params[ring];
+    memset(&P, 0, sizeof(P));
+    P.K = make_params(e, d_in, d_out, n);
+    P.K.work_counter = &w.ctl->work_counter;
+    P.K.start = d_start;
+    int M = (n + 31) / 32 * 32;
+    if (M > w.capacity) M = w.capacity;
+    P.M = M;
+    P.max_rounds = 4096 + 8 * (int)(((long long)n + M) / (M + 1)) * 1024;    // safety net: a patch needs <= ~1000 evaluations
+    P.ctx = w.ctx; P.tiles = w.tiles; P.fval = w.fval; P.sstate = w.sstate; P.eval_list = w.eval_list; P.post_list = w.post_list;
+    P.ctl = w.ctl;
+    P.cond = w.cond;
+    P.use_cond = (e->wf_mode == 1) ? 1 : 0;
+    P.round_log = w.round_log; P.round_log_cap = 65536;
+    HP_CUDA(cudaMemcpyAsync(w.d_params, &P, sizeof(P), cudaMemcpyHostToDevice, s));
+    HP_CUDA(cudaMemsetAsync(w.ctl, 0, sizeof(hp::WfCtl), s));
+    if (M > 0) HP_CUDA(cudaMemsetAsync(w.sstate, 0, sizeof(int) * (size_t)M, s));
+    HP_CUDA(cudaEventRecord(w.h_params_free[ring], s));
+    return 0;
+}
+
+// A batch is cut into up to wf_parts contiguous sub-batches, each with its own round loop (own slots, lists, WHILE node) in ONE graph.
+// Every round of a sub-batch is a chain of latency-bound kernels (ncu: the SMs are > 85 % idle during an advance kernel), so the
+// branches interleave on the GPU: while one sub-batch is in its optimizer phase others sample.
+static int launch_wavefront(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, hpmvs_patch_t* d_out, cudaStream_t s) {
+    const double* d_start = e->next_start;
+    e->next_start = nullptr;
+    hpmvs_engine::WfBatch& b = e->wfb[e->wf_seq++ % 2];
+    int rc;
+    for (int k = 0; k < e->wf_parts; k++) if ((rc = wf_ensure_context(e, b.part[k]))) return rc;
+    if (!b.done) HP_CUDA(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
+    if (e->wf_mode == 1 && (rc = wf_build_graph(e, b))) return rc;
+    int parts = (e->wf_mode == 1) ? e->wf_parts : 1;                 // host-loop mode (debugging) drives one loop
+    int used = parts;
+    while (used > 1 && n / used < 2048) used--;                      // small batches are not cut further
+    HP_CUDA(cudaStreamWaitEvent(s, b.done, 0));                      // the previous launch on this batch context has left its buffers
+    HP_CUDA(cudaEventRecord(e->ev0, s));
+    for (int k = 0; k < parts; k++) {
+        const int a = k < used ? (int)((long long)n * k / used) : n, z = k < used ? (int)((long long)n * (k + 1) / used) : n;
+        if ((rc = wf_prepare_part(e, b.part[k], z - a, d_in + a, d_out + a, d_start ? d_start + 2 * (size_t)a : nullptr, s))) return rc;
+    }
+    if (e->wf_mode == 1) {
+        HP_CUDA(cudaGraphLaunch(b.exec, s));
+        e->launches += (unsigned long long)used * (e->wf_split ? 7 : 5);    // kernels of a graph branch (fill + one round); rounds are counted on the device
+    } else {
+        hpmvs_engine::WfContext& w = b.part[0];
+        const WfLaunchShape sh = wf_shape(e, w);
+        hp::wf_post_kernel<true><<<sh.grid_s, hp::WF_SAMPLER_WARPS * 32, sh.smem_s, s>>>(w.d_params);
+        e->launches++;
+        const int max_rounds = w.h_params[(w.seq + 1) % 2]->max_rounds;
+        for (int live = 1, guard = 0; live && guard < max_rounds; guard += 4) {
+            for (int r = 0; r < 4; r++) wf_enqueue_round(e, w, s);
+            e->launches += 4 * (e->wf_split ? 6 : 4);
+            HP_CUDA(cudaMemcpyAsync(w.h_ctl, w.ctl, sizeof(hp::WfCtl), cudaMemcpyDeviceToHost, s));
+            HP_CUDA(cudaStreamSynchronize(s));
+            live = w.h_ctl->live;
+        }
+    }
+    for (int k = 0; k < parts; k++) HP_CUDA(cudaMemcpyAsync(b.part[k].h_ctl, b.part[k].ctl, sizeof(hp::WfCtl), cudaMemcpyDeviceToHost, s));
+    HP_CUDA(cudaEventRecord(e->ev1, s));
+    HP_CUDA(cudaEventRecord(b.done, s));
+    HP_CUDA(cudaGetLastError());
+    return 0;
+}
+
 static int launch_optimize(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, hpmvs_patch_t* d_out, cudaStream_t s) {
     int rc = check_ready(e);
     if (rc) return rc;
     rc = sync_cameras(e);
     if (rc) return rc;
+    if (e->wf_mode != 0) return launch_wavefront(e, n, d_in, d_out, s);
     // launches on different streams overlap (a CTA of the next launch starts on an SM as soon as the previous launch's CTA
     // there has drained its slots): every launch gets its own work counter from a small ring; a ring slot is reused only after
     // the launch that used it last has completed
@@ -769,6 +1013,28 @@ int hpmvs_engine_download_depth(hpmvs_engine_t* e, int cam, int level, float* ou
     *rows = (int)(e->h_cams[cam].h[level] / 2.0); *cols = (int)(e->h_cams[cam].w[level] / 2.0);
     if (out) HP_CUDA(cudaMemcpy(out, e->depths[cam][level], sizeof(float) * (size_t)(*rows) * (*cols), cudaMemcpyDeviceToHost));
     return 0;
+}
+
+// debugging aid (not in the header): writes the per-round log of the most recent wavefront launch as CSV (needs HPMVS_WF_LOG at create)
+int hpmvs_engine_dump_round_log(hpmvs_engine_t* e, const char* path) {
+    if (!e || !path) return HPMVS_E_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    HP_CUDA(cudaSetDevice(e->device));
+    HP_CUDA(cudaDeviceSynchronize());
+    hpmvs_engine::WfContext& w = e->wfb[(e->wf_seq + 1) % 2].part[0];
+    if (!w.round_log) return HPMVS_E_STATE;
+    hp::WfCtl c;
+    HP_CUDA(cudaMemcpy(&c, w.ctl, sizeof(c), cudaMemcpyDeviceToHost));
+    const int n = c.round < 65536 ? c.round : 65536;
+    std::vector<unsigned long long> h((size_t)4 * n);
+    HP_CUDA(cudaMemcpy(h.data(), w.round_log, sizeof(unsigned long long) * 4 * n, cudaMemcpyDeviceToHost));
+    FILE* fh = fopen(path, "w");
+    if (!fh) return HPMVS_E_ARG;
+    fprintf(fh, "round,us,evals,posts,dead\n");
+    for (int i = 0; i < n; i++)
+        fprintf(fh, "%d,%.3f,%llu,%llu,%llu\n", i, i ? (h[4 * i] - h[0]) / 1e3 : 0.0, h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+    fclose(fh);
+    return n;
 }
 
 int hpmvs_engine_counters(hpmvs_engine_t* e, hpmvs_counters_t* out, int reset) {

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/hpmvs_b200.h"
+#include "undistort_math.h"
 
 struct hpmvs_nvm {
     struct Cam { std::string filename; double f, q[4], c[3], r; };
@@ -189,36 +190,10 @@ int hpmvs_undistort_rgb(const uint8_t* rgb, int width, int height, double f_in, 
             x /= f_;
             y /= f_;
             if (y == 0) y = 1e-3;
-            float mx, my;
-            {
-                const double t2 = y * y;
-                const double t3 = t2 * t2 * t2;
-                const double t4 = x * x;
-                const double t7 = k1_ * (t2 + t4);
-                if (k1_ > 0) {
-                    const double t8 = 1.0 / t7;
-                    const double t10 = t3 / (t7 * t7);
-                    const double t14 = sqrt(t10 * (0.25 + t8 / 27.0));
-                    const double t15 = t2 * t8 * y * 0.5;
-                    const double t17 = pow(t14 + t15, 1.0 / 3.0);
-                    const double t18 = t17 - t2 * t8 / (t17 * 3.0);
-                    mx = t18 * x / y;
-                    my = t18;
-                } else {
-                    const double t9 = t3 / (t7 * t7 * 4.0);
-                    const double t11 = t3 / (t7 * t7 * t7 * 27.0);
-                    const std::complex<double> t12 = t9 + t11;
-                    const std::complex<double> t13 = sqrt(t12);
-                    const double t14 = t2 / t7;
-                    const double t15 = t14 * y * 0.5;
-                    const std::complex<double> t16 = t13 + t15;
-                    const std::complex<double> t17 = pow(t16, 1.0 / 3.0);
-                    const std::complex<double> t18 = (t17 + t14 / (t17 * 3.0)) * std::complex<double>(0.0, sqrt(3.0));
-                    const std::complex<double> t19 = -0.5 * (t17 + t18) + t14 / (t17 * 6.0);
-                    mx = t19.real() * x / y;
-                    my = t19.real();
-                }
-            }
+            // source position in the distorted image (undistort_math.h: Cardano's root, the reference's operations in its order)
+            const double kr = k1_ * ((double)(y * y) + (double)(x * x));
+            const ud::Source src = (k1_ > 0) ? ud::source_positive_k1(x, y, kr) : ud::source_negative_k1_host(x, y, kr);
+            const float mx = src.mx, my = src.my;
             x = mx * (float)f_ + width / 2.0f;
             y = my * (float)f_ + height / 2.0f;
             if (x > 1 && x < width - 1 && y > 1 && y < height - 1) {

@@ -25,6 +25,7 @@
 #include "../../include/hpmvs_b200.h"
 #define BQ_STATE_IN_SHARED 1
 #include "bobyqa3.h"
+#include "undistort_math.h"
 
 namespace hp {
 
@@ -1549,6 +1550,43 @@ __global__ void rgbx_to_rgb_kernel(const uchar4* __restrict__ src, int pitch, in
     const uchar4 p = src[(size_t)y * pitch + x];
     unsigned char* d = dst + 3 * ((size_t)y * w + x);
     d[0] = p.x; d[1] = p.y; d[2] = p.z;
+}
+
+// Image::undistort (src/hpmvs/Image.cpp:68-149) on the device: one thread per TARGET pixel finds its source position in the distorted
+// level-0 image in closed form (undistort_math.h), samples it with CImg's _linear_atXY (thirdLibs/cimg/CImg.h:12218-12235, f32) when
+// it lies strictly inside the 1-pixel border, and truncates to u8; other target pixels are 0 (the reference leaves them
+// uninitialised, Q13).  `src` is the tightly packed interleaved RGB staging copy, `dst` the pitched RGBX level 0.
+__global__ void undistort_kernel(const unsigned char* __restrict__ src, int w, int h, float f, float k1, uchar4* __restrict__ dst, int pitch) {
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ix >= w || iy >= h) return;
+    float y = (float)((double)iy - (double)h / 2.0);
+    float x = (float)((double)ix - (double)w / 2.0);
+    x /= f;
+    y /= f;
+    if (y == 0.0f) y = (float)1e-3;
+    const double kr = (double)k1 * ((double)(y * y) + (double)(x * x));
+    const ud::Source s = (k1 > 0.0f) ? ud::source_positive_k1(x, y, kr) : ud::source_negative_k1_polar(x, y, kr);
+    x = s.mx * f + (float)w / 2.0f;
+    y = s.my * f + (float)h / 2.0f;
+    uchar4 o = make_uchar4(0, 0, 0, 255);
+    if (x > 1.0f && x < (float)(w - 1) && y > 1.0f && y < (float)(h - 1)) {
+        const unsigned px = (unsigned)x, py = (unsigned)y;
+        const float dx = x - (float)px, dy = y - (float)py;
+        const unsigned nx = dx > 0.0f ? px + 1 : px, ny = dy > 0.0f ? py + 1 : py;
+        const unsigned char* a = src + 3 * ((size_t)py * w + px);
+        const unsigned char* b = src + 3 * ((size_t)py * w + nx);
+        const unsigned char* c = src + 3 * ((size_t)ny * w + px);
+        const unsigned char* d = src + 3 * ((size_t)ny * w + nx);
+        unsigned char r[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            const float Icc = (float)a[ch], Inc = (float)b[ch], Icn = (float)c[ch], Inn = (float)d[ch];
+            const float v = Icc + dx * (Inc - Icc + dy * (Icc + Inn - Icn - Inc)) + dy * (Icn - Icc);
+            r[ch] = (unsigned char)v;
+        }
+        o = make_uchar4(r[0], r[1], r[2], 255);
+    }
+    dst[(size_t)iy * pitch + ix] = o;
 }
 
 // CImg::get_resize_halfXY (thirdLibs/cimg/CImg.h:21189-21203): 3x3 mask at odd (x,y), Neumann border,

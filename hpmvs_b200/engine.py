@@ -64,6 +64,7 @@ def _lib():
         L.hpmvs_engine_destroy.argtypes = [vp]; L.hpmvs_engine_destroy.restype = None
         L.hpmvs_engine_set_cameras.argtypes = [vp, C.c_int, C.POINTER(Camera)]
         L.hpmvs_engine_upload_image.argtypes = [vp, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_size_t]
+        L.hpmvs_engine_upload_image_undistort.argtypes = [vp, C.c_int, u8p, C.c_int, C.c_int, C.c_size_t, C.c_double, C.c_double]
         L.hpmvs_engine_build_pyramid.argtypes = [vp, C.c_int]
         L.hpmvs_engine_download_image.argtypes = [vp, C.c_int, C.c_int, u8p, C.c_size_t]
         L.hpmvs_engine_set_covis.argtypes = [vp, ip, ip]
@@ -181,6 +182,12 @@ class Engine:
         h, w = rgb.shape[:2]
         _check(_lib().hpmvs_engine_upload_image(self._h, cam, level, _p(rgb, C.c_uint8), w, h, 3 * w))
 
+    def upload_image_undistort(self, cam: int, rgb: np.ndarray, f: float, r: float) -> None:
+        """Image::load's undistortion (Image.cpp:51-53, :68-149) on the GPU: distorted level-0 image in, undistorted level 0 resident."""
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        h, w = rgb.shape[:2]
+        _check(_lib().hpmvs_engine_upload_image_undistort(self._h, cam, _p(rgb, C.c_uint8), w, h, 3 * w, float(f), float(r)))
+
     def build_pyramid(self, cam: int) -> None:
         _check(_lib().hpmvs_engine_build_pyramid(self._h, cam))
 
@@ -197,17 +204,22 @@ class Engine:
         _check(_lib().hpmvs_engine_set_covis(self._h, _p(offs, C.c_int32), _p(ids, C.c_int32)))
 
     @classmethod
-    def from_synth(cls, scene, options: Optional[Options] = None, device: int = 0, compat_covis: bool = True) -> "Engine":
+    def from_synth(cls, scene, options: Optional[Options] = None, device: int = 0, compat_covis: bool = True,
+                   undistort: str = "host") -> "Engine":
         """NVM cameras + level-0 images of a hpmvs_b200.synth.SynthScene -> resident scene (pyramids built on the GPU)."""
         e = cls(options, device)
         ml = e.options.maxlevel
         cams = [camera_from_nvm(c.f, c.q, c.c, img.shape[1], img.shape[0], ml) for c, img in zip(scene.cameras, scene.images)]
         e.set_cameras(cams)
         for i, img in enumerate(scene.images):
-            if getattr(scene.cameras[i], "r", 0.0) != 0.0:          # Image::load undistorts level 0 first (Image.cpp:51-53)
-                from . import io as _io
-                img = _io.undistort(img, scene.cameras[i].f, scene.cameras[i].r)
-            e.upload_image(i, 0, img)
+            r = getattr(scene.cameras[i], "r", 0.0)
+            if r != 0.0 and undistort == "gpu":                      # Image::load undistorts level 0 first (Image.cpp:51-53)
+                e.upload_image_undistort(i, img, scene.cameras[i].f, r)
+            else:
+                if r != 0.0:
+                    from . import io as _io
+                    img = _io.undistort(img, scene.cameras[i].f, r)    # host twin, same libm as the reference: bit-exact
+                e.upload_image(i, 0, img)
             e.build_pyramid(i)
         e.set_covis(extract_covis(len(cams), scene.meas_offsets, scene.meas_cam, compat_covis))
         return e

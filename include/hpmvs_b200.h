@@ -117,6 +117,14 @@ int  hpmvs_engine_set_cameras(hpmvs_engine_t *e, int n, const hpmvs_camera_t *ca
 int  hpmvs_engine_upload_image(hpmvs_engine_t *e, int cam, int level, const uint8_t *rgb, int w, int h,
                                size_t pitch_bytes);
 
+/* Replaces Image::load's undistortion step (Image.cpp:51-53 -> Image::undistort, :68-149) on the GPU: `rgb` is the DISTORTED level-0
+ * image of view `cam` (focal length f, VisualSFM radial parameter r from the NVM camera line); level 0 on the device becomes the
+ * undistorted image (target pixels without a source are 0).  r == 0: plain upload.  The source positions are computed with CUDA's
+ * double-precision libm: identical to the host function hpmvs_undistort_rgb() except for rare last-place roundings (<= 1 grey level on
+ * < 0.01 % of the pixels, tests/test_next_rows.py). */
+int  hpmvs_engine_upload_image_undistort(hpmvs_engine_t *e, int cam, const uint8_t *rgb, int w, int h, size_t pitch_bytes,
+                                         double f, double r);
+
 /* Optional replacement for Image::load's pyramid loop (Image.cpp:56-57, CImg get_resize_halfXY): builds
  * levels 1..maxlevel of view `cam` on the GPU from the already uploaded level 0 (bit-exact with CImg). */
 int  hpmvs_engine_build_pyramid(hpmvs_engine_t *e, int cam);

@@ -40,6 +40,21 @@ def bq3():
         r = L.bq3_run_testfunc(fid, p(x0), p(lb), p(ub), xtol, maxeval, p(xo), C.byref(fo), p(tx), p(tf), cap, C.byref(ne))
         n = min(ne.value, cap)
         return r, xo, fo.value, tx[:n].copy(), tf[:n].copy(), L.bq3_last_rescues()
+
+    L.bq3_run_testfunc_tile.argtypes = L.bq3_run_testfunc.argtypes + [C.c_int, C.c_int, C.POINTER(C.c_int)]
+
+    def run_tile(fid, x0, lb, ub, xtol=1e-7, maxeval=1000, lane=0, split=True):
+        """Same optimiser on lane `lane` of a 32-state tile (bq3::StateTile), advanced phase by phase like the wavefront kernels."""
+        x0 = np.asarray(x0, float); lb = np.asarray(lb, float); ub = np.asarray(ub, float)
+        xo = np.zeros(3); fo = C.c_double(); ne = C.c_int(); ny = C.c_int(); cap = maxeval + 8
+        tx = np.zeros((cap, 3)); tf = np.zeros(cap)
+        p = lambda a: a.ctypes.data_as(dp)
+        r = L.bq3_run_testfunc_tile(fid, p(x0), p(lb), p(ub), xtol, maxeval, p(xo), C.byref(fo), p(tx), p(tf), cap, C.byref(ne),
+                                    lane, 1 if split else 0, C.byref(ny))
+        n = min(ne.value, cap)
+        return r, xo, fo.value, tx[:n].copy(), tf[:n].copy(), L.bq3_last_rescues(), ny.value
+    run.tile = run_tile
+    run.tile_bytes = L.bq3_tile_bytes()
     return run
 
 
@@ -87,3 +102,27 @@ def test_fuzz_including_rescue_and_roundoff(bq3):
         rescues += got[5] > 0
     assert results.get(-4, 0) > 0 and results.get(5, 0) > 0 and results.get(1, 0) > 0 and results.get(4, 0) > 0
     assert rescues > 10      # the RESCUE branch really ran, and still matched
+
+
+def test_tiled_state_and_phase_split_visit_the_same_points(bq3):
+    """The wavefront kernels keep 32 optimiser states interleaved in one tile (bq3::StateTile: every member a 256-byte cell, lane l's
+    value at byte 8*l) and advance them phase by phase (A: absorb the objective value, T: trust-region step, B: shift / geometry step /
+    Lagrange values), yielding in front of every heavy block of another phase.  Same points, same result, on every lane, and no
+    byte outside the lane's own column is touched."""
+    assert bq3.tile_bytes % 256 == 0 and bq3.tile_bytes // 256 >= 200
+    rng = np.random.default_rng(1)
+    yields = 0
+    for k, fid in enumerate([0, 1, 2, 3, 5, 8] + list(range(100, 160)) + list(range(5000, 5060))):
+        if fid == 0:
+            x0, lb, ub = [1.0, 10.5, 1.1], [0.9, 9, 0.9], [1.2, 11.2, 1.2]
+        else:
+            x0 = [rng.normal(0, 0.3), rng.uniform(-23.9, 23.9), rng.uniform(-23.9, 23.9)] if fid % 2 else [0, 0, 0]
+            lb, ub = HP_LB, HP_UB
+        want = bq3(fid, x0, lb, ub, 1e-7, 1000)
+        for split in (False, True):
+            got = bq3.tile(fid, x0, lb, ub, 1e-7, 1000, lane=(7 * k) % 32, split=split)
+            assert got[0] != -1000, "a neighbouring lane's bytes were written"
+            assert _same(want[:5], got), (fid, split)
+            assert got[5] == want[5]
+            yields += got[6]
+    assert yields > 1000

@@ -399,3 +399,37 @@ def test_city100_full_size_against_the_reference_path():
     assert int((got0["status"] == 13).sum()) == 0 and int((got0["status"] == 0).sum()) > 1000
     print(f"city100: {len(seeds)} seeds, {int(ok.sum())} optimized, bit-exact {bit.mean():.5f}, max views {int(got['nimages'][ok].max())} "
           f"(compat=0: {int(got0['nimages'][got0['status'] == 0].max())})")
+
+
+@pytest.mark.parametrize("mode,split,slots", [(2, 1, 0), (2, 0, 128), (1, 1, 0), (1, 0, 0), (1, 1, 128)])
+def test_wavefront_variant_bit_exact(plane, monkeypatch, mode, split, slots):
+    """The wavefront form of the fused path (patch_kernels_wf.cuh: one kernel per phase of a refinement round, optimizer states in
+    32-state tiles in HBM/L2, the rounds driven by a CUDA-graph WHILE node - mode 1 - or by the host - mode 2) must return the same
+    bytes as the persistent kernel and the oracle; with fewer slots than patches the slots are refilled as patches retire."""
+    sc, orc, seeds, eng = plane
+    monkeypatch.setenv("HPMVS_WF", str(mode))
+    monkeypatch.setenv("HPMVS_WF_SPLIT", str(split))
+    if slots:
+        monkeypatch.setenv("HPMVS_WF_SLOTS", str(slots))
+    eng_w = hp.Engine.from_synth(sc)
+    pe = to_engine(seeds)
+    monkeypatch.setenv("HPMVS_WF", "0")
+    a = hp.Engine.from_synth(sc).optimize(pe)
+    eng_w.counters(reset=True)
+    b = eng_w.optimize(pe)
+    c = eng_w.counters(reset=True)
+    assert a.tobytes() == b.tobytes()
+    assert c.patches == len(pe) and c.patches_ok == int((b["status"] == 0).sum()) and c.evals == int(b["evals"].sum()) and c.textures == int(b["textures"].sum())
+    assert eng_w.optimize(pe).tobytes() == a.tobytes()          # the graph is relaunched on its second context
+    assert eng_w.optimize(pe[:5]).tobytes() == a[:5].tobytes()  # tiny batch: most slots never receive a patch
+    eng_w.set_start_mode(True)
+    monkeypatch.setenv("HPMVS_WF", "0")
+    e0 = hp.Engine.from_synth(sc); e0.set_start_mode(True)
+    assert eng_w.optimize(pe).tobytes() == e0.optimize(pe).tobytes()
+    oracle.set_cr_asinf(True)
+    try:
+        ref = orc.optimize_batch(seeds, nthreads=8)
+    finally:
+        oracle.set_cr_asinf(False)
+    st = compare_outputs(ref, b)
+    assert st["status_equal"] == st["n"] and st["bit_exact"] == st["both_ok"] and st["vis_equal"] == st["both_ok"]
