@@ -50,7 +50,7 @@ inline void h_normalized3(const float* a, float* o) {
 
 enum { HP_RING = 4, HP_WF_PARTS = 8 };
 #ifndef HP_WF_DEFAULT_MODE
-#define HP_WF_DEFAULT_MODE 0
+#define HP_WF_DEFAULT_MODE (-1)     // auto: wavefront kernels for large batches, the persistent kernel below wf_min_batch patches
 #endif
 
 struct hpmvs_engine {
@@ -65,6 +65,7 @@ struct hpmvs_engine {
     std::vector<hp::DevCamera> h_cams;
     std::vector<std::vector<LevelImage>> images;   // [cam][level]
     std::vector<std::vector<float*>> depths;        // [cam][level] Scene::m_depths
+    std::vector<std::vector<size_t>> depth_cells;   // [cam][level] floats allocated (a camera table with other image sizes reallocates)
     int* d_accept = nullptr;
     size_t cap_accept = 0;
     hp::DevCamera* d_cams = nullptr;
@@ -105,9 +106,10 @@ struct hpmvs_engine {
     cudaEvent_t pool_done[2] = {nullptr, nullptr};
     unsigned long long parked_seq = 0;
     // wavefront form of the fused path (patch_kernels_wf.cuh): 0 = persistent kernels, 1 = per-phase kernels in a CUDA-graph WHILE loop,
-    // 2 = the same kernels launched round by round from the host (debugging; the call blocks)
+    // 2 = the same kernels launched round by round from the host (debugging; the call blocks), -1 = 1 for batches >= wf_min_batch else 0
     int wf_mode = 0;
-    int wf_split = 1;                // 1: advance phases A / T / B as three kernels, 0: one kernel with every phase
+    int wf_min_batch = 20000;        // measured cross-over (profiles/r2_wavefront_experiments.md): 10 k patches 19 ms persistent vs 24 ms wavefront
+    int wf_split = 0;                // 1: advance phases A / T / B as three kernels, 0: one kernel with every phase (default: 61.5 vs 71.7 ms per city100 step)
     int wf_capacity = 0;             // slots in flight per wavefront context
     struct WfContext {
         int capacity = 0;
@@ -127,7 +129,7 @@ struct hpmvs_engine {
         cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
         cudaEvent_t done = nullptr;
     } wfb[2];
-    int wf_parts = 4;                // a batch is cut into up to this many sub-batches: their round loops interleave on the GPU
+    int wf_parts = 1;                // a batch is cut into up to this many sub-batches: their round loops interleave on the GPU
     unsigned long long wf_seq = 0;
     unsigned long long wf_overruns = 0;
     std::mutex mu;
@@ -192,6 +194,16 @@ static int check_ready(hpmvs_engine* e) {
         for (int l = 0; l < nl && l < HPMVS_LEVELS; l++)
             if (!e->images[c][l].data) return HPMVS_E_STATE;
     return 0;
+}
+
+// view ids index the camera table on the device: every host-buffer entry point rejects out-of-range ids instead of faulting there
+static bool valid_view_ids(const hpmvs_engine* e, int n, const hpmvs_patch_t* in) {
+    for (int i = 0; i < n; i++) {
+        const int k = in[i].nimages < HPMVS_MAX_VIEWS ? in[i].nimages : HPMVS_MAX_VIEWS;
+        for (int j = 0; j < k; j++)
+            if (in[i].images[j] < 0 || in[i].images[j] >= e->ncams) return false;
+    }
+    return true;
 }
 
 static hp::KParams make_params(hpmvs_engine* e, const hpmvs_patch_t* d_in, hpmvs_patch_t* d_out, int n) {
@@ -278,6 +290,7 @@ int hpmvs_engine_create(const hpmvs_options_t* opt, int device, hpmvs_engine_t**
     e->wf_mode = HP_WF_DEFAULT_MODE;
     if (const char* wf = getenv("HPMVS_WF")) e->wf_mode = atoi(wf);
     if (const char* ws = getenv("HPMVS_WF_SPLIT")) e->wf_split = atoi(ws);
+    if (const char* wm = getenv("HPMVS_WF_MIN_BATCH")) e->wf_min_batch = atoi(wm);
     e->wf_capacity = e->sm_count * 12 * 32;                                 // one full wave of advance threads (12 warps per SM)
     if (const char* wp = getenv("HPMVS_WF_PARTS")) e->wf_parts = atoi(wp);
     if (e->wf_parts < 1) e->wf_parts = 1;
@@ -546,13 +559,14 @@ static int wf_ensure_context(hpmvs_engine* e, hpmvs_engine::WfContext& w) {
     return 0;
 }
 
-struct WfLaunchShape { dim3 grid_s, grid_a; size_t smem_s; };
+struct WfLaunchShape { dim3 grid_s, grid_p, grid_a; size_t smem_s; };
 static WfLaunchShape wf_shape(const hpmvs_engine* e, const hpmvs_engine::WfContext& w) {
     WfLaunchShape sh;
     sh.smem_s = sizeof(hp::NccWarp) * hp::WF_SAMPLER_WARPS;
     int per_sm = 7 / e->wf_parts;                                      // 7 CTAs x 4 warps x 7 KB per SM, shared by the sub-batches in flight
     if (per_sm < 2) per_sm = 2;
     sh.grid_s = dim3((unsigned)(e->sm_count * per_sm));
+    sh.grid_p = dim3((unsigned)(e->sm_count * (per_sm > 4 ? 4 : per_sm)));   // post pass: dynamic tickets; most rounds it has nothing to do
     sh.grid_a = dim3((unsigned)(w.capacity / hp::WF_ADV_THREADS));
     return sh;
 }
@@ -568,8 +582,7 @@ static void wf_enqueue_round(const hpmvs_engine* e, const hpmvs_engine::WfContex
         hp::wf_advance_kernel<bq3::PH_ALL><<<sh.grid_a, hp::WF_ADV_THREADS, 0, s>>>(w.d_params);
     }
     hp::wf_eval_kernel<<<sh.grid_s, hp::WF_SAMPLER_WARPS * 32, sh.smem_s, s>>>(w.d_params);
-    hp::wf_post_kernel<false><<<sh.grid_s, hp::WF_SAMPLER_WARPS * 32, sh.smem_s, s>>>(w.d_params);
-    hp::wf_sched_kernel<<<1, 1, 0, s>>>(w.d_params);
+    hp::wf_post_kernel<false><<<sh.grid_p, hp::WF_SAMPLER_WARPS * 32, sh.smem_s, s>>>(w.d_params);
 }
 
 static int wf_build_graph(hpmvs_engine* e, hpmvs_engine::WfBatch& b) {
@@ -609,8 +622,7 @@ static int wf_build_graph(hpmvs_engine* e, hpmvs_engine::WfBatch& b) {
             HP_CUDA(chain((void*)hp::wf_advance_kernel<bq3::PH_ALL>, sh.grid_a, hp::WF_ADV_THREADS, 0));
         }
         HP_CUDA(chain((void*)hp::wf_eval_kernel, sh.grid_s, hp::WF_SAMPLER_WARPS * 32, sh.smem_s));
-        HP_CUDA(chain((void*)hp::wf_post_kernel<false>, sh.grid_s, hp::WF_SAMPLER_WARPS * 32, sh.smem_s));
-        HP_CUDA(chain((void*)hp::wf_sched_kernel, dim3(1), 1, 0));
+        HP_CUDA(chain((void*)hp::wf_post_kernel<false>, sh.grid_p, hp::WF_SAMPLER_WARPS * 32, sh.smem_s));
     }
     HP_CUDA(cudaGraphInstantiate(&b.exec, b.graph, 0));
     return 0;
@@ -634,7 +646,7 @@ static int wf_prepare_part(hpmvs_engine* e, hpmvs_engine::WfContext& w, int n, c
     P.ctx = w.ctx; P.tiles = w.tiles; P.fval = w.fval; P.sstate = w.sstate; P.eval_list = w.eval_list; P.post_list = w.post_list;
     P.ctl = w.ctl;
     P.cond = w.cond;
-    P.use_cond = (e->wf_mode == 1) ? 1 : 0;
+    P.use_cond = (e->wf_mode != 2) ? 1 : 0;
     P.round_log = w.round_log; P.round_log_cap = 65536;
     HP_CUDA(cudaMemcpyAsync(w.d_params, &P, sizeof(P), cudaMemcpyHostToDevice, s));
     HP_CUDA(cudaMemsetAsync(w.ctl, 0, sizeof(hp::WfCtl), s));
@@ -653,8 +665,9 @@ static int launch_wavefront(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, h
     int rc;
     for (int k = 0; k < e->wf_parts; k++) if ((rc = wf_ensure_context(e, b.part[k]))) return rc;
     if (!b.done) HP_CUDA(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
-    if (e->wf_mode == 1 && (rc = wf_build_graph(e, b))) return rc;
-    int parts = (e->wf_mode == 1) ? e->wf_parts : 1;                 // host-loop mode (debugging) drives one loop
+    const bool graph_mode = e->wf_mode != 2;
+    if (graph_mode && (rc = wf_build_graph(e, b))) return rc;
+    int parts = graph_mode ? e->wf_parts : 1;                        // host-loop mode (debugging) drives one loop
     int used = parts;
     while (used > 1 && n / used < 2048) used--;                      // small batches are not cut further
     HP_CUDA(cudaStreamWaitEvent(s, b.done, 0));                      // the previous launch on this batch context has left its buffers
@@ -663,9 +676,9 @@ static int launch_wavefront(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, h
         const int a = k < used ? (int)((long long)n * k / used) : n, z = k < used ? (int)((long long)n * (k + 1) / used) : n;
         if ((rc = wf_prepare_part(e, b.part[k], z - a, d_in + a, d_out + a, d_start ? d_start + 2 * (size_t)a : nullptr, s))) return rc;
     }
-    if (e->wf_mode == 1) {
+    if (graph_mode) {
         HP_CUDA(cudaGraphLaunch(b.exec, s));
-        e->launches += (unsigned long long)used * (e->wf_split ? 7 : 5);    // kernels of a graph branch (fill + one round); rounds are counted on the device
+        e->launches += (unsigned long long)used * (e->wf_split ? 6 : 4);    // kernels of a graph branch (fill + one round); rounds are counted on the device
     } else {
         hpmvs_engine::WfContext& w = b.part[0];
         const WfLaunchShape sh = wf_shape(e, w);
@@ -674,7 +687,7 @@ static int launch_wavefront(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, h
         const int max_rounds = w.h_params[(w.seq + 1) % 2]->max_rounds;
         for (int live = 1, guard = 0; live && guard < max_rounds; guard += 4) {
             for (int r = 0; r < 4; r++) wf_enqueue_round(e, w, s);
-            e->launches += 4 * (e->wf_split ? 6 : 4);
+            e->launches += 4 * (e->wf_split ? 5 : 3);
             HP_CUDA(cudaMemcpyAsync(w.h_ctl, w.ctl, sizeof(hp::WfCtl), cudaMemcpyDeviceToHost, s));
             HP_CUDA(cudaStreamSynchronize(s));
             live = w.h_ctl->live;
@@ -692,7 +705,7 @@ static int launch_optimize(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, hp
     if (rc) return rc;
     rc = sync_cameras(e);
     if (rc) return rc;
-    if (e->wf_mode != 0) return launch_wavefront(e, n, d_in, d_out, s);
+    if (e->wf_mode > 0 || (e->wf_mode < 0 && n >= e->wf_min_batch)) return launch_wavefront(e, n, d_in, d_out, s);
     // launches on different streams overlap (a CTA of the next launch starts on an SM as soon as the previous launch's CTA
     // there has drained its slots): every launch gets its own work counter from a small ring; a ring slot is reused only after
     // the launch that used it last has completed
@@ -794,12 +807,7 @@ int hpmvs_optimize_batch(hpmvs_engine_t* e, int n, const hpmvs_patch_t* in, hpmv
     if (rc) return rc;
     rc = ensure_patch_capacity(e, (size_t)n);
     if (rc) return rc;
-    // view ids index the camera table on the device: reject out-of-range ids here instead of faulting there
-    for (int i = 0; i < n; i++) {
-        const int k = in[i].nimages < HPMVS_MAX_VIEWS ? in[i].nimages : HPMVS_MAX_VIEWS;
-        for (int j = 0; j < k; j++)
-            if (in[i].images[j] < 0 || in[i].images[j] >= e->ncams) return HPMVS_E_ARG;
-    }
+    if (!valid_view_ids(e, n, in)) return HPMVS_E_ARG;
     HP_CUDA(cudaMemcpyAsync(e->d_in, in, sizeof(hpmvs_patch_t) * n, cudaMemcpyHostToDevice, s));
     if (e->start_mode == 1) {
         // the one libm-dependent scalar step of the path, evaluated where the reference evaluates it: on the host
@@ -835,11 +843,7 @@ int hpmvs_optimize_batch_submit(hpmvs_engine_t* e, int n, const hpmvs_patch_t* i
     cudaStream_t s = (cudaStream_t)stream;
     int rc = check_ready(e);
     if (rc) return rc;
-    for (int i = 0; i < n; i++) {
-        const int k = in[i].nimages < HPMVS_MAX_VIEWS ? in[i].nimages : HPMVS_MAX_VIEWS;
-        for (int j = 0; j < k; j++)
-            if (in[i].images[j] < 0 || in[i].images[j] >= e->ncams) return HPMVS_E_ARG;
-    }
+    if (!valid_view_ids(e, n, in)) return HPMVS_E_ARG;
     hpmvs_engine::Stage& st = e->stage2[e->submit_seq++ % 2];
     if (!st.done) HP_CUDA(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
     if ((size_t)n > st.cap) {
@@ -883,6 +887,7 @@ int hpmvs_ncc_batch(hpmvs_engine_t* e, int n, const hpmvs_patch_t* in, int ref_i
     cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
     int rc = check_ready(e);
     if (rc) return rc;
+    if (!valid_view_ids(e, n, in)) return HPMVS_E_ARG;
     rc = sync_cameras(e);
     if (rc) return rc;
     rc = ensure_patch_capacity(e, (size_t)n);
@@ -939,13 +944,16 @@ int hpmvs_engine_depth_reset(hpmvs_engine_t* e) {
     if ((int)e->depths.size() != e->ncams) {
         for (auto& cam : e->depths) for (auto* d : cam) if (d) cudaFree(d);
         e->depths.assign(e->ncams, std::vector<float*>(HPMVS_LEVELS, nullptr));
+        e->depth_cells.assign(e->ncams, std::vector<size_t>(HPMVS_LEVELS, 0));
         e->cams_dirty = true;
     }
+    if ((int)e->depth_cells.size() != e->ncams) e->depth_cells.assign(e->ncams, std::vector<size_t>(HPMVS_LEVELS, 0));
     for (int c = 0; c < e->ncams; c++)
         for (int l = 0; l < nl; l++) {
             const size_t rows = (size_t)(int)(e->h_cams[c].h[l] / 2.0), cols = (size_t)(int)(e->h_cams[c].w[l] / 2.0);
             const size_t cnt = rows * cols > 0 ? rows * cols : 1;
-            if (!e->depths[c][l]) { HP_CUDA(cudaMalloc(&e->depths[c][l], cnt * sizeof(float))); e->cams_dirty = true; }
+            if (e->depths[c][l] && e->depth_cells[c][l] != cnt) { cudaFree(e->depths[c][l]); e->depths[c][l] = nullptr; }
+            if (!e->depths[c][l]) { HP_CUDA(cudaMalloc(&e->depths[c][l], cnt * sizeof(float))); e->depth_cells[c][l] = cnt; e->cams_dirty = true; }
             hp::depth_fill_kernel<<<(unsigned)((cnt + 255) / 256 > 1024 ? 1024 : (cnt + 255) / 256), 256, 0, e->stream>>>(e->depths[c][l], cnt);
             e->launches++;
         }
@@ -959,19 +967,23 @@ static int ensure_depths(hpmvs_engine* e) {
     return HPMVS_E_STATE;
 }
 
-int hpmvs_depth_set_batch(hpmvs_engine_t* e, int n, const hpmvs_patch_t* patches, void* stream) {
+static int depth_set_impl(hpmvs_engine_t* e, int n, const hpmvs_patch_t* patches, void* stream, int subtract);
+int hpmvs_depth_set_batch(hpmvs_engine_t* e, int n, const hpmvs_patch_t* patches, void* stream) { return depth_set_impl(e, n, patches, stream, 0); }
+int hpmvs_depth_unset_batch(hpmvs_engine_t* e, int n, const hpmvs_patch_t* patches, void* stream) { return depth_set_impl(e, n, patches, stream, 1); }
+static int depth_set_impl(hpmvs_engine_t* e, int n, const hpmvs_patch_t* patches, void* stream, int subtract) {
     if (!e || n < 0 || (n > 0 && !patches)) return HPMVS_E_ARG;
     if (n == 0) return 0;
     std::lock_guard<std::mutex> lk(e->mu);
     HP_CUDA(cudaSetDevice(e->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
     int rc = ensure_depths(e); if (rc) return rc;
+    if (!valid_view_ids(e, n, patches)) return HPMVS_E_ARG;
     rc = sync_cameras(e); if (rc) return rc;
     rc = ensure_patch_capacity(e, (size_t)n); if (rc) return rc;
     HP_CUDA(cudaMemcpyAsync(e->d_in, patches, sizeof(hpmvs_patch_t) * n, cudaMemcpyHostToDevice, s));
     const hp::KParams K = make_params(e, e->d_in, e->d_out, n);
     const int total = n * HPMVS_MAX_VIEWS;
-    hp::depth_set_kernel<<<(total + 255) / 256, 256, 0, s>>>(K, e->d_in, n);
+    hp::depth_set_kernel<<<(total + 255) / 256, 256, 0, s>>>(K, e->d_in, n, subtract);
     e->launches++;
     HP_CUDA(cudaGetLastError());
     HP_CUDA(cudaStreamSynchronize(s));
@@ -985,6 +997,7 @@ int hpmvs_accept_batch(hpmvs_engine_t* e, int n, const hpmvs_patch_t* patches, f
     HP_CUDA(cudaSetDevice(e->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
     int rc = ensure_depths(e); if (rc) return rc;
+    if (!valid_view_ids(e, n, patches)) return HPMVS_E_ARG;
     rc = sync_cameras(e); if (rc) return rc;
     rc = ensure_patch_capacity(e, (size_t)n); if (rc) return rc;
     if ((size_t)n * 3 > e->cap_accept) {

@@ -1425,8 +1425,9 @@ __device__ __forceinline__ int round_px(float a, float b) { return (int)((double
 // integer pixel / DEPTH_SUBSAMPLE (a double 2): f64 quotient, truncation
 __device__ __forceinline__ int sub2(int v) { return (int)((double)v / 2.0); }
 
-// setDepths(patch, false) for every (patch, view) pair; the reference's "d < old -> old = d" is an atomic float min
-__global__ void depth_set_kernel(const KParams K, const hpmvs_patch_t* __restrict__ patches, int n) {
+// setDepths(patch, subtract) for every (patch, view) pair; the reference's "d < old -> old = d" is an atomic float min, its
+// "old == d -> MAX_DEPTH" (subtract, Scene.cpp:372-373) an atomic compare-and-swap on the same bits
+__global__ void depth_set_kernel(const KParams K, const hpmvs_patch_t* __restrict__ patches, int n, int subtract) {
     const int total = n * MAXV;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
         const hpmvs_patch_t& p = patches[t / MAXV];
@@ -1443,7 +1444,9 @@ __global__ void depth_set_kernel(const KParams K, const hpmvs_patch_t* __restric
         const float d = imgC.z;
         if (!(d >= 0.0f)) continue;
         if (x < 0 || x >= cam.dcols[level] || y < 0 || y >= cam.drows[level]) continue;
-        atomicMin(reinterpret_cast<int*>(cam.depth[level] + (size_t)y * cam.dcols[level] + x), __float_as_int(d));
+        int* cell = reinterpret_cast<int*>(cam.depth[level] + (size_t)y * cam.dcols[level] + x);
+        if (subtract) atomicCAS(cell, __float_as_int(d), __float_as_int(MAX_DEPTH));
+        else atomicMin(cell, __float_as_int(d));
     }
 }
 

@@ -8,7 +8,7 @@
 //                           the geometry step / forms the Lagrange values (B) and emits the next point       (lane = patch)
 //       eval              : objective at the emitted points: 7x7 gather in every view + NCC                  (warp = patch)
 //       post              : finished refinements: stages after the refinement, result record, slot refill    (warp = patch)
-//       sched             : one thread: list bookkeeping + loop condition
+//                           + (last CTA) list bookkeeping and the loop condition
 //
 // Why: in the persistent kernel both roles are latency bound with 12 warps per SM (2 optimizer warps walking ~100 KB of FP64 code,
 // 10 sampler warps; profiles/r1_cycle_breakdown.md, r2_cycle_dump_city100_r1kernel.txt) and every extra optimizer warp slowed the
@@ -41,6 +41,7 @@ struct WfCtl {
     int round;
     int live;              // != 0 while another round is needed (host-loop mode reads it back)
     int overrun;           // set when max_rounds was hit with live slots (never expected; reported by the host)
+    int ctas_done;         // post kernel: CTAs that have finished this round (the last one runs wf_sched)
     int run_post;          // sched's decision for the NEXT round: the post kernel runs (it is latency bound: ~100 us even for one patch)
 };
 
@@ -63,6 +64,12 @@ struct WfParams {
 
 constexpr int WF_SAMPLER_WARPS = 4;    // eval / post / fill kernels: 4 warps x 7 KB scratch per CTA (7 CTAs = 28 warps per SM)
 constexpr int WF_ADV_THREADS = 128;    // advance kernels: 4 tiles per CTA
+#ifndef WF_ADV_MIN_CTAS
+#define WF_ADV_MIN_CTAS 4              // 128 registers: 61.1 vs 64.9 ms per city100 step against the uncapped 162 (profiles/r2_wavefront_experiments.md)
+#endif
+#ifndef WF_PREFETCH
+#define WF_PREFETCH 0              // measured neutral (city100 61.6 vs 62.3 ms per step): the optimizer is bound by its own dependent chains
+#endif
 
 __device__ __forceinline__ bq3::StateTile& wf_state(const WfParams& P, int slot) {
     return *reinterpret_cast<bq3::StateTile*>(P.tiles + (size_t)(slot >> 5) * sizeof(bq3::StateTile) + (size_t)(slot & 31) * 8);
@@ -81,6 +88,33 @@ __device__ __forceinline__ void wf_push(int* list, int* cnt, bool pred, int slot
     if (pred) list[base + __popc(m & ((1u << lane) - 1u))] = slot;
 }
 
+// ---- sched: end of a round (run by the last CTA of the post kernel) ----------------------------------------------------------------
+__device__ __forceinline__ void wf_sched(const WfParams& P) {
+    WfCtl& c = *P.ctl;
+    if (P.round_log && c.round < P.round_log_cap) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        unsigned long long* r = P.round_log + 4 * (size_t)c.round;
+        r[0] = t; r[1] = (unsigned long long)c.eval_cnt; r[2] = (unsigned long long)c.post_cnt; r[3] = (unsigned long long)c.dead;
+    }
+    c.eval_cnt = 0;
+    if (c.run_post) { c.post_cnt = 0; c.post_ticket = 0; }     // the post pass of this round consumed the list
+    c.round = c.round + 1;
+    // Post passes are batched: a pass costs the latency of one post-stage (several scoring evaluations per patch, ~100-200 us) whether
+    // it serves one patch or ten thousand, so finished patches are collected and served when nothing else is left to do, or - while
+    // input patches are still waiting for a slot - when enough slots (1/16) have piled up to be worth a refill pass.
+    const int pending = c.post_cnt;
+    const int active = P.M - c.dead - pending;
+    const bool more_input = c.work_counter < P.K.n;
+    int thr = P.M / 16;
+    if (thr < 64) thr = 64;
+    c.run_post = (pending > 0 && (active <= 0 || (more_input && pending >= thr))) ? 1 : 0;
+    int live = (c.dead < P.M) ? 1 : 0;
+    if (live && c.round >= P.max_rounds) { live = 0; c.overrun = 1; }
+    c.live = live;
+    if (P.use_cond) cudaGraphSetConditional(P.cond, live ? 1u : 0u);
+}
+
 // ---- fill (round 0: all slots) and post (finished refinements + refill): warp = patch --------------------------------------------
 template <bool FILL>
 __global__ void __launch_bounds__(WF_SAMPLER_WARPS * 32) wf_post_kernel(const WfParams* __restrict__ Pp) {
@@ -91,11 +125,11 @@ __global__ void __launch_bounds__(WF_SAMPLER_WARPS * 32) wf_post_kernel(const Wf
     Scratch& W = WS.S;
     LaneCtx& C = WS.P;
     const int lane = threadIdx.x & 31;
-    if (!FILL && !P.ctl->run_post) return;             // finished patches wait in post_list until sched asks for a post pass
-    const int count = FILL ? P.M : P.ctl->post_cnt;
+    // finished patches wait in post_list until sched asks for a post pass
+    const int count = FILL ? P.M : (P.ctl->run_post ? P.ctl->post_cnt : 0);
     unsigned long long cnt[4] = {0, 0, 0, 0};
     int ndead = 0;
-    for (;;) {
+    while (count > 0) {                                  // (a round without a post pass must not draw tickets)
         int t = 0;
         if (lane == 0) t = atomicAdd(FILL ? &P.ctl->fill_ticket : &P.ctl->post_ticket, 1);
         t = __shfl_sync(FULL, t, 0);
@@ -121,6 +155,18 @@ __global__ void __launch_bounds__(WF_SAMPLER_WARPS * 32) wf_post_kernel(const Wf
         if (cnt[0]) {
             atomicAdd(&K.counters[0], cnt[0]); atomicAdd(&K.counters[1], cnt[1]);
             atomicAdd(&K.counters[2], cnt[2]); atomicAdd(&K.counters[3], cnt[3]);
+        }
+    }
+    if (!FILL) {
+        // the post kernel closes the round: its last CTA to finish does the bookkeeping and sets the loop condition
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(&P.ctl->ctas_done, 1) == (int)gridDim.x - 1) {
+                P.ctl->ctas_done = 0;
+                __threadfence();
+                wf_sched(P);
+            }
         }
     }
 }
@@ -156,7 +202,7 @@ __global__ void __launch_bounds__(WF_SAMPLER_WARPS * 32) wf_eval_kernel(const Wf
 
 // ---- advance: BOBYQA, lane = patch slot, one kernel per phase (bq3::PH_A / PH_T / PH_B, or PH_ALL in one) ----------------------------
 template <unsigned PHASES>
-__global__ void __launch_bounds__(WF_ADV_THREADS) wf_advance_kernel(const WfParams* __restrict__ Pp) {
+__global__ void __launch_bounds__(WF_ADV_THREADS, WF_ADV_MIN_CTAS) wf_advance_kernel(const WfParams* __restrict__ Pp) {
     const WfParams& P = *Pp;
     const KParams& K = P.K;
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -169,6 +215,16 @@ __global__ void __launch_bounds__(WF_ADV_THREADS) wf_advance_kernel(const WfPara
     if (take) {
         LaneCtx& mine = P.ctx[slot];
         bq3::StateTile& bq = wf_state(P, slot);
+#if WF_PREFETCH
+        // every kernel starts with a cold L1: without this each first touch of a state member is a dependent L2 round trip (~210 of
+        // them per round); issued up front they overlap, and the optimizer's own accesses then hit L1
+        if (st0 != WS_NEW) {
+            const char* base = reinterpret_cast<const char*>(&bq);
+#pragma unroll 1
+            for (int c = 0; c < (int)(sizeof(bq3::StateTile) / (8 * BQ_TILE_LANES)); c++)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (size_t)c * 8 * BQ_TILE_LANES));
+        }
+#endif
         double xcur[3] = {0.0, 0.0, 0.0};
         int act;
         if (st0 == WS_NEW) {
@@ -206,32 +262,5 @@ __global__ void __launch_bounds__(WF_ADV_THREADS) wf_advance_kernel(const WfPara
     wf_push(P.post_list, &P.ctl->post_cnt, st == WS_POST, slot);
 }
 
-// ---- sched: end of a round ---------------------------------------------------------------------------------------------------------
-__global__ void wf_sched_kernel(const WfParams* __restrict__ Pp) {
-    const WfParams& P = *Pp;
-    WfCtl& c = *P.ctl;
-    if (P.round_log && c.round < P.round_log_cap) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        unsigned long long* r = P.round_log + 4 * (size_t)c.round;
-        r[0] = t; r[1] = (unsigned long long)c.eval_cnt; r[2] = (unsigned long long)c.post_cnt; r[3] = (unsigned long long)c.dead;
-    }
-    c.eval_cnt = 0;
-    if (c.run_post) { c.post_cnt = 0; c.post_ticket = 0; }     // the post kernel of this round consumed the list
-    c.round = c.round + 1;
-    // Post passes are batched: a pass costs the latency of one post-stage (several scoring evaluations per patch, ~100-200 us) whether
-    // it serves one patch or ten thousand, so finished patches are collected and served when nothing else is left to do, or - while
-    // input patches are still waiting for a slot - when enough slots (1/16) have piled up to be worth a refill pass.
-    const int pending = c.post_cnt;
-    const int active = P.M - c.dead - pending;
-    const bool more_input = c.work_counter < P.K.n;
-    int thr = P.M / 16;
-    if (thr < 64) thr = 64;
-    c.run_post = (pending > 0 && (active <= 0 || (more_input && pending >= thr))) ? 1 : 0;
-    int live = (c.dead < P.M) ? 1 : 0;
-    if (live && c.round >= P.max_rounds) { live = 0; c.overrun = 1; }
-    c.live = live;
-    if (P.use_cond) cudaGraphSetConditional(P.cond, live ? 1u : 0u);
-}
 
 }  // namespace hp

@@ -84,6 +84,7 @@ def _lib():
         L.hpmvs_extract_covis.argtypes = [C.c_int, C.c_int, ip, ip, C.c_int, ip, ip, C.c_int]
         L.hpmvs_engine_depth_reset.argtypes = [vp]
         L.hpmvs_depth_set_batch.argtypes = [vp, C.c_int, vp, vp]
+        L.hpmvs_depth_unset_batch.argtypes = [vp, C.c_int, vp, vp]
         L.hpmvs_accept_batch.argtypes = [vp, C.c_int, vp, C.c_float, ip, vp]
         L.hpmvs_engine_download_depth.argtypes = [vp, C.c_int, C.c_int, fp, ip, ip]
         L.hpmvs_expand_candidates.argtypes = [C.c_int, C.POINTER(Camera), C.c_int, vp, fp, C.c_int, vp]
@@ -280,6 +281,11 @@ class Engine:
         """n x Scene::setDepths(patch, false) for the records with status OK."""
         assert patches.dtype == PATCH_DTYPE and patches.flags.c_contiguous
         _check(_lib().hpmvs_depth_set_batch(self._h, len(patches), patches.ctypes.data, None))
+
+    def depth_unset(self, patches: np.ndarray) -> None:
+        """n x Scene::setDepths(patch, true): depth cells that still hold exactly these patches' depths go back to MAX_DEPTH."""
+        assert patches.dtype == PATCH_DTYPE and patches.flags.c_contiguous
+        _check(_lib().hpmvs_depth_unset_batch(self._h, len(patches), patches.ctypes.data, None))
 
     def accept(self, patches: np.ndarray, margin: float = 1.0) -> np.ndarray:
         """[n,3] = depthTests, viewBlockTest, pixelFreeTests per patch (Scene.cpp:518-644)."""

@@ -183,6 +183,9 @@ int  hpmvs_engine_depth_reset(hpmvs_engine_t *e);
 /* Replaces n calls of Scene::setDepths(patch, false) (Scene.cpp:351-381) for the records with status == HPMVS_OK;
  * the "smaller depth wins" update is an atomic float min on the device. */
 int  hpmvs_depth_set_batch(hpmvs_engine_t *e, int n, const hpmvs_patch_t *patches, void *stream);
+/* Replaces n calls of Scene::setDepths(patch, true) (Scene.cpp:351-381, :372-373) - a patch leaves the tree (CellProcessor::filter :76,
+ * ::branch :273): every depth cell that still holds exactly this patch's depth goes back to MAX_DEPTH (atomic compare-and-swap). */
+int  hpmvs_depth_unset_batch(hpmvs_engine_t *e, int n, const hpmvs_patch_t *patches, void *stream);
 /* Replaces, per patch, Scene::depthTests / viewBlockTest / pixelFreeTests (Scene.cpp:518-644) as used by
  * CellProcessor::extend (src/hpmvs/CellProcessor.cpp:134-142): out[3*i+0..2] = the three counts. */
 int  hpmvs_accept_batch(hpmvs_engine_t *e, int n, const hpmvs_patch_t *patches, float margin, int32_t *out, void *stream);
@@ -209,7 +212,20 @@ typedef struct hpmvs_pipeline_params {
     const hpmvs_camera_t *cams;    /* the cameras the engine was given (candidate construction runs on the host) */
     int32_t shard_count;           /* multi-GPU: > 1 = this call grows only the cells of tree level shard_level dealt to shard_rank; */
     int32_t shard_rank;            /*   0 or 1 = everything.  Merge the ranks' results with an NCCL gather + hpmvs_dedup_border. */
-    int32_t shard_level;           /*   (<= start_level) */
+    int32_t shard_level;           /*   (<= start_level; used when there is no sub-tree table: cells of that level dealt out by a hash) */
+    int32_t minlevel;              /* HpmvsOptions::MINLEVEL (0): a patch whose views are all at pyramid level <= minlevel is exhausted and
+                                      never branches (Scene::getLevelSupport, CellProcessor.cpp:222-225) */
+    /* sub-tree table from hpmvs_shard_subtrees() (the reference's getSubTrees split): sub-tree i is the cell sub_key[3i..3i+2] of tree
+     * level sub_level[i] and belongs to rank sub_rank[i]; space outside every sub-tree belongs to nobody.  nsub == 0: hash by shard_level. */
+    int32_t nsub;
+    const int32_t *sub_level;
+    const int64_t *sub_key;
+    const int32_t *sub_rank;
+    /* per-step border hand-off between ranks (CellProcessor.cpp:147-153, distributeBorderCell :487-540): called by EVERY rank the same
+     * number of times with the records it accepted in this step; *recv must point at the concatenation of all ranks' records in rank
+     * order (valid until the next call), *n_recv their number.  NULL: no hand-off (a patch that leaves the rank's cells is dropped). */
+    int (*exchange)(void *user, int n_send, const hpmvs_patch_t *send, hpmvs_patch_t **recv, int *n_recv);
+    void *exchange_user;
 } hpmvs_pipeline_params_t;
 typedef struct hpmvs_pipeline_stats {
     int64_t optimize_calls, optimized_ok;
@@ -217,6 +233,7 @@ typedef struct hpmvs_pipeline_stats {
     int32_t nlevels;
     int32_t level[HPMVS_PIPELINE_MAX_LEVELS];
     int64_t extended[HPMVS_PIPELINE_MAX_LEVELS], branched[HPMVS_PIPELINE_MAX_LEVELS];
+    int64_t exchanged;             /* records received through the exchange callback */
 } hpmvs_pipeline_stats_t;
 /* seeds: candidate patches as hpmvs_seed_patches() builds them.  *out receives a malloc'ed array of *nout final patches
  * (release with hpmvs_free).  Resets the engine's depth maps first. */
@@ -238,6 +255,10 @@ int  hpmvs_root_cube(int n, const hpmvs_patch_t *patches, double origin[3], doub
  * cell_of[i] / rank_of[i] = sub-tree / rank of patch i (-1 outside the cube).  Returns the number of sub-trees. */
 int  hpmvs_shard_cells(int n, const hpmvs_patch_t *patches, const double origin[3], double root_width, int min_subtrees, int nranks,
                        int32_t *cell_of, int32_t *rank_of);
+/* The same split as a table for hpmvs_pipeline_params_t: sub-tree i = cell sub_key[3i..3i+2] of tree level sub_level[i], dealt to rank
+ * sub_rank[i].  Arrays need room for `cap` sub-trees; returns their number (or -needed when cap is too small). */
+int  hpmvs_shard_subtrees(int n, const hpmvs_patch_t *patches, const double origin[3], double root_width, int min_subtrees, int nranks,
+                          int cap, int32_t *sub_level, int64_t *sub_key, int32_t *sub_rank);
 
 /* ---- host-side scene surface (plain C++ on the host, no GPU needed): what feeds the engine ---- */
 

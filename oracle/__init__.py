@@ -97,6 +97,7 @@ def lib():
         L.orc_set_cr_asinf.argtypes = [C.c_int]
         L.orc_depth_reset.argtypes = [vp]
         L.orc_depth_set_batch.argtypes = [vp, C.c_int, C.c_void_p]
+        L.orc_depth_unset_batch.argtypes = [vp, C.c_int, C.c_void_p]
         L.orc_get_depth.restype = C.POINTER(C.c_float); L.orc_get_depth.argtypes = [vp, C.c_int, C.c_int, ip, ip]
         L.orc_accept_batch.argtypes = [vp, C.c_int, C.c_void_p, C.c_float, ip]
         L.orc_expand_candidates.argtypes = [vp, C.c_int, C.c_void_p, fp, C.c_int, C.c_void_p]
@@ -213,6 +214,11 @@ class OracleScene:
     def depth_set(self, patches: np.ndarray) -> None:
         p = np.ascontiguousarray(patches)
         lib().orc_depth_set_batch(self._h, len(p), p.ctypes.data)
+
+    def depth_unset(self, patches: np.ndarray) -> None:
+        """Scene::setDepths(patch, true) (Scene.cpp:351-381) for the records with status OK."""
+        p = np.ascontiguousarray(patches)
+        lib().orc_depth_unset_batch(self._h, len(p), p.ctypes.data)
 
     def depth(self, cam: int, level: int) -> np.ndarray:
         r, c = C.c_int32(), C.c_int32()

@@ -650,8 +650,9 @@ void alloc_depths(Scene& s) {
     }
 }
 
-// Scene::setDepths(patch, false) (Scene.cpp:351-381)
-void set_depths(Scene& s, const orc_patch_t& p) {
+// Scene::setDepths(patch, subtract) (Scene.cpp:351-381): subtract == false keeps the smaller depth; subtract == true resets the cell to
+// MAX_DEPTH when it still holds exactly this patch's depth (a patch that is removed from the tree: CellProcessor.cpp:76, :273)
+void set_depths(Scene& s, const orc_patch_t& p, bool subtract = false) {
     const V4 c{{p.center[0], p.center[1], p.center[2], p.center[3]}};
     for (int k = 0; k < p.nimages; k++) {
         const int idx = p.images[k];
@@ -665,7 +666,8 @@ void set_depths(Scene& s, const orc_patch_t& p) {
         DepthMap& m = s.depths[idx][level];
         if (x < 0 || x >= m.cols || y < 0 || y >= m.rows) continue;
         float& old = m.d[(size_t)y * m.cols + x];
-        if (d < old) old = d;
+        if (old == d && subtract) old = MAX_DEPTH;
+        else if (!subtract && d < old) old = d;
     }
 }
 
@@ -1041,6 +1043,11 @@ void orc_depth_set_batch(void* scene, int n, const orc_patch_t* patches) {
     Scene& s = *static_cast<Scene*>(scene);
     if (s.depths.size() != s.cameras.size()) alloc_depths(s);
     for (int i = 0; i < n; i++) if (patches[i].status == ORC_OK) set_depths(s, patches[i]);
+}
+void orc_depth_unset_batch(void* scene, int n, const orc_patch_t* patches) {
+    Scene& s = *static_cast<Scene*>(scene);
+    if (s.depths.size() != s.cameras.size()) alloc_depths(s);
+    for (int i = 0; i < n; i++) if (patches[i].status == ORC_OK) set_depths(s, patches[i], true);
 }
 const float* orc_get_depth(void* scene, int cam, int level, int* rows, int* cols) {
     Scene& s = *static_cast<Scene*>(scene);

@@ -111,6 +111,7 @@ void  orc_patch_color(void *scene, const orc_patch_t *patch, float rgb[3]);
 /* --- "next" rows: the steps right after optimize() in CellProcessor::extend (CellProcessor.cpp:134-142,197-201) --- */
 void  orc_depth_reset(void *scene);                                           /* Scene.cpp:74-81 */
 void  orc_depth_set_batch(void *scene, int n, const orc_patch_t *patches);    /* setDepths(p,false) for status==OK */
+void  orc_depth_unset_batch(void *scene, int n, const orc_patch_t *patches);  /* setDepths(p,true) for status==OK */
 const float *orc_get_depth(void *scene, int cam, int level, int *rows, int *cols);
 /* out[3*i+0..2] = depthTests, viewBlockTest, pixelFreeTests (Scene.cpp:518-644) */
 void  orc_accept_batch(void *scene, int n, const orc_patch_t *patches, float margin, int32_t *out);

@@ -76,6 +76,7 @@ def lib():
         L.refh_init_patches.argtypes = [vp, C.c_void_p, C.c_int]
         L.refh_depth_reset.argtypes = [vp]
         L.refh_depth_set_batch.argtypes = [vp, C.c_int, C.c_void_p]
+        L.refh_depth_unset_batch.argtypes = [vp, C.c_int, C.c_void_p]
         L.refh_get_depth.argtypes = [vp, C.c_int, C.c_int, fp, C.c_int, ip, ip]
         L.refh_accept_batch.argtypes = [vp, C.c_int, C.c_void_p, C.c_float, ip]
         _lib = L
@@ -167,6 +168,10 @@ class RefScene:
 
     def depth_reset(self) -> None:
         lib().refh_depth_reset(self._h)
+
+    def depth_unset(self, patches: np.ndarray) -> None:
+        p = np.ascontiguousarray(patches)
+        lib().refh_depth_unset_batch(self._h, len(p), p.ctypes.data)
 
     def depth_set(self, patches: np.ndarray) -> None:
         p = np.ascontiguousarray(patches)

@@ -181,6 +181,15 @@ void refh_depth_reset(void* h) {
     RefScene* s = static_cast<RefScene*>(h);
     for (auto& cam : s->scene.m_depths) for (auto& m : cam) *m = Eigen::MatrixXf::Ones(m->rows(), m->cols()) * mo3d::Scene::MAX_DEPTH;
 }
+void refh_depth_unset_batch(void* h, int n, const orc_patch_t* patches) {
+    RefScene* s = static_cast<RefScene*>(h);
+    for (int i = 0; i < n; i++) {
+        if (patches[i].status != 0) continue;
+        mo3d::Patch3d p;
+        to_patch3d(patches[i], p);
+        s->scene.setDepths(p, true);
+    }
+}
 void refh_depth_set_batch(void* h, int n, const orc_patch_t* patches) {
     RefScene* s = static_cast<RefScene*>(h);
     for (int i = 0; i < n; i++) {
