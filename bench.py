@@ -50,7 +50,7 @@ def parse_args(argv=None):
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="city100", choices=["city100", "plane8", "plane8x100k", "city500_4k", "city24", "tiny"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="patches in the cpu_baseline sample (0 = auto)")
-    ap.add_argument("--inflight", type=int, default=2, help="steps in flight (each on its own stream): >1 lets the next step's CTAs start on SMs the previous step has drained")
+    ap.add_argument("--inflight", type=int, default=4, help="steps in flight (each on its own stream): >1 lets the next step's CTAs start on SMs the previous step has drained")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-ncc", action="store_true", help="skip the stand-alone scoring kernel leg (profiling runs)")
     return ap.parse_args(argv)
@@ -294,9 +294,18 @@ def main():
 
     # ---- scene replicated on every GPU; seed batch: sharded by octree sub-tree (strong) or one draw per rank (weak) ----------------
     t_setup0 = time.perf_counter()
-    scene, desc = cached_scene(args.workload, rank)
     opts = hp.Options.defaults()
-    eng = hp.Engine.from_synth(scene, opts, device=local_rank)
+    if args.workload == "city500_4k":
+        # 500 x 4K level-0 images are 12 GB: rendered, uploaded and dropped one view at a time (never pickled, never all on the host)
+        from hpmvs_b200 import synth
+        synth.USE_GPU_RENDERER = True
+        nv = int(os.environ.get("HPMVS_CITY500_VIEWS", "500")); ns = int(os.environ.get("HPMVS_CITY500_SEEDS", "400000"))
+        desc = f"{nv}-view 4K synthetic city block, {ns // 1000}k seed points (BASELINE.json configs[4])"
+        eng, scene = hp.Engine.from_stream(lambda sink: synth.city_scene(n_views=nv, width=3840, height=2160, focal=3000.0, n_seeds=ns,
+                                                                         seed=5, name="city500v", image_sink=sink), opts, device=local_rank)
+    else:
+        scene, desc = cached_scene(args.workload, rank)
+        eng = hp.Engine.from_synth(scene, opts, device=local_rank)
     t_upload = time.perf_counter() - t_setup0
     seeds_all, valid = hp.seed_patches(opts, eng.cameras, scene.points, scene.meas_offsets, scene.meas_cam)
     seeds_all = np.ascontiguousarray(seeds_all[valid])
@@ -384,22 +393,36 @@ def main():
     merged = [0, 0]
     gather_s = [0.0]
 
+    dedup_cell = float(np.median(seeds_all["scale"])) * 2.0        # one patch per cell of the tree level the seeds are inserted at
+    d_nkeep = torch.zeros(1, dtype=torch.int32, device="cuda")
+    gstream = torch.cuda.Stream()                                  # the exchange runs beside the next step's kernels
+
     def collect(k):
         streams[k % F].synchronize()
         out_k = h_outs[k % F].numpy().view(hp.PATCH_DTYPE).reshape(n)
         okc = int((out_k["status"] == 0).sum())
         if dist is not None and strong:
             tg = time.perf_counter()
-            allr, owner = gather.gather_to_root(out_k[out_k["status"] == 0])
-            if rank == 0:
-                keep = gather.dedup_border(allr, owner, cell=float(np.median(allr["scale"])) if len(allr) else 1.0,
-                                           origin=shard_info["origin"])
-                merged[0], merged[1] = int(len(allr)), int(len(keep))
+            with torch.cuda.stream(gstream):
+                # the step's records go back to the device once (pinned, 4.6 MB per 22 k patches), the accepted ones are compacted
+                # there, gathered onto rank 0 over NCCL send/recv and de-duplicated there by the engine's kernels
+                d_res = h_outs[k % F].to("cuda", non_blocking=True)
+                mine = d_res[d_res.view(torch.int32)[:, gather.STATUS_WORD] == 0]
+                allr, owner = gather.gather_to_root_device(mine)
+                if rank == 0:
+                    keep = torch.empty(len(allr), dtype=torch.uint8, device="cuda")
+                    eng.dedup_border_device(len(allr), allr.data_ptr(), owner.data_ptr(), shard_info["origin"], dedup_cell,
+                                            keep.data_ptr(), d_nkeep.data_ptr(), gstream.cuda_stream)
+                    merged[0], merged[1] = int(len(allr)), int(d_nkeep.item())       # the D2H read of the step's result
+            gstream.synchronize()
             gather_s[0] += time.perf_counter() - tg
         return okc
 
     for k in range(2):
         eng.optimize_submit(n, h_ins[k % F].data_ptr(), h_outs[k % F].data_ptr(), streams[k % F].cuda_stream)
+    for k in range(2):
+        collect(k)            # warm-up of the exchange as well: NCCL sets up its send/recv connections on first use (hundreds of ms)
+    gather_s[0] = 0.0
     barrier()
     t0 = time.perf_counter()
     ok_e2e = 0
@@ -483,7 +506,7 @@ def main():
                 return None
         # CPU baseline on a bounded sample of the same batch (rank 0)
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and len(scene.images) > 0:              # (the streamed 500-view scene keeps no host images: no CPU leg)
             threads = host_threads()
             sample = args.cpu_sample or int(min(len(seeds_all), max(512, 3000 * threads)))
             rate, dt, okc, ns, kind, how = cpu_reference_rate(scene, to_oracle(seeds_all), sample, threads)
@@ -501,7 +524,8 @@ def main():
                                        f"patch shards x{world}, scene replicated, no data-path collective",
                         "shards": shard_info, "wall_s_timed_region": t_wall, "e2e_gather_dedup_ms_per_step": 1e3 * gather_max / args.steps,
                         "patches_gathered_kept": merged if dist is not None and strong else None,
-                        "scene_upload_s": t_upload, "hbm_used_gb": hbm_used_gb},
+                        "scene_upload_s": t_upload, "scene_upload_note": "render + upload + pyramid, streamed view by view" if args.workload == "city500_4k" else "upload + pyramid",
+                        "hbm_used_gb": hbm_used_gb},
                 "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": "patches/s", "h2d_bytes_per_step": int(n * (REC_BYTES + 16)), "d2h_bytes_per_step": int(n * REC_BYTES),
                         "ms_per_step": 1e3 * t_e2e_max / args.steps, "start_mode": 1},

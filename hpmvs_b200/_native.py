@@ -22,7 +22,7 @@ HEADERS = [os.path.join(_HERE, "csrc", "patch_kernels.cuh"), os.path.join(_HERE,
 # patch_kernels.cuh); FMA contraction would change roundings and break the reproducible BOBYQA trajectory.
 # -DBQ_DEFER_TRUST=1: a second trust-region step inside one optimizer round is deferred to the next round (bobyqa3.h)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false", "-DBQ_DEFER_TRUST=1",
-              "-Xcompiler", "-fPIC,-ffp-contract=off", "-diag-suppress", "550,177", "-shared"]
+              "-Xcompiler", "-fPIC,-ffp-contract=off", "-diag-suppress", "550,177", "-shared", "-ldl"]
 
 
 def _stale() -> bool:

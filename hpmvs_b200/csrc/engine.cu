@@ -11,8 +11,17 @@
 #include <mutex>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "patch_kernels.cuh"
 #include "patch_kernels_wf.cuh"
+
+// NVTX ranges around the host-visible steps of a batch (tracing): free when no profiler is attached
+struct HpNvtxRange {
+    explicit HpNvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~HpNvtxRange() { nvtxRangePop(); }
+};
+#define HP_NVTX(name) HpNvtxRange hp_nvtx_range_##__LINE__(name)
 
 #define HP_CUDA(call)                                                                                   \
     do {                                                                                                \
@@ -48,7 +57,7 @@ inline void h_normalized3(const float* a, float* o) {
 
 }  // namespace
 
-enum { HP_RING = 4, HP_WF_PARTS = 8 };
+enum { HP_RING = 4, HP_WF_PARTS = 8, HP_WF_BATCHES = 8 };   // wavefront: up to 8 launches in flight, each with its own slots
 #ifndef HP_WF_DEFAULT_MODE
 #define HP_WF_DEFAULT_MODE (-1)     // auto: wavefront kernels for large batches, the persistent kernel below wf_min_batch patches
 #endif
@@ -68,6 +77,8 @@ struct hpmvs_engine {
     std::vector<std::vector<size_t>> depth_cells;   // [cam][level] floats allocated (a camera table with other image sizes reallocates)
     int* d_accept = nullptr;
     size_t cap_accept = 0;
+    unsigned char* d_dedup = nullptr;   // hash table + per-record slots of hpmvs_dedup_border_device
+    size_t cap_dedup = 0;
     hp::DevCamera* d_cams = nullptr;
     bool cams_dirty = true;
     int* d_covis_off = nullptr;
@@ -80,7 +91,7 @@ struct hpmvs_engine {
     size_t cap_patches = 0, cap_inccs = 0;
     // hpmvs_optimize_batch_submit: a second staging set so that two host-buffer batches can be in flight
     struct Stage { hpmvs_patch_t* d_in = nullptr; hpmvs_patch_t* d_out = nullptr; size_t cap = 0; double* d_start = nullptr;
-                   double* h_start = nullptr; size_t cap_start = 0; cudaEvent_t done = nullptr; } stage2[2];
+                   double* h_start = nullptr; size_t cap_start = 0; cudaEvent_t done = nullptr; } stage2[8];
     unsigned long long submit_seq = 0;
     int start_mode = 0;              // hpmvs_engine_set_start_mode
     double* d_start = nullptr;       // host-evaluated start angles of the batch (start_mode 1)
@@ -128,7 +139,7 @@ struct hpmvs_engine {
         WfContext part[HP_WF_PARTS];
         cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
         cudaEvent_t done = nullptr;
-    } wfb[2];
+    } wfb[HP_WF_BATCHES];
     int wf_parts = 1;                // a batch is cut into up to this many sub-batches: their round loops interleave on the GPU
     unsigned long long wf_seq = 0;
     unsigned long long wf_overruns = 0;
@@ -316,7 +327,7 @@ void hpmvs_engine_destroy(hpmvs_engine_t* e) {
     for (auto& cam : e->depths)
         for (auto* d : cam)
             if (d) cudaFree(d);
-    cudaFree(e->d_accept);
+    cudaFree(e->d_accept); cudaFree(e->d_dedup);
     for (int i = 0; i < 2; i++) if (e->pool_done[i]) cudaEventDestroy(e->pool_done[i]);
     cudaFree(e->d_cams); cudaFree(e->d_covis_off); cudaFree(e->d_covis_ids);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_inccs); cudaFree(e->d_stage);
@@ -513,6 +524,7 @@ int hpmvs_engine_set_covis(hpmvs_engine_t* e, const int32_t* offsets, const int3
 // std::asin(float), std::cos(double), std::acos(double) - the reference's own calls, so that the engine starts every
 // optimisation from exactly the reference's x[1], x[2] whatever libm the reference was linked against.
 static void host_start_parameters(hpmvs_engine* e, int n, const hpmvs_patch_t* in, double* out) {
+    HP_NVTX("hpmvs:host_start_parameters (libm asin/acos per patch)");
     const double lb = -23.99999, ub = 23.99999;                 // optimizePatch's bounds (:333-340)
     const float angle_scale = (float)(M_PI / 48.0f);            // :398
     for (int i = 0; i < n; i++) {
@@ -661,7 +673,7 @@ static int wf_prepare_part(hpmvs_engine* e, hpmvs_engine::WfContext& w, int n, c
 static int launch_wavefront(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, hpmvs_patch_t* d_out, cudaStream_t s) {
     const double* d_start = e->next_start;
     e->next_start = nullptr;
-    hpmvs_engine::WfBatch& b = e->wfb[e->wf_seq++ % 2];
+    hpmvs_engine::WfBatch& b = e->wfb[e->wf_seq++ % HP_WF_BATCHES];
     int rc;
     for (int k = 0; k < e->wf_parts; k++) if ((rc = wf_ensure_context(e, b.part[k]))) return rc;
     if (!b.done) HP_CUDA(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
@@ -701,6 +713,7 @@ static int launch_wavefront(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, h
 }
 
 static int launch_optimize(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, hpmvs_patch_t* d_out, cudaStream_t s) {
+    HP_NVTX("hpmvs:launch_optimize");
     int rc = check_ready(e);
     if (rc) return rc;
     rc = sync_cameras(e);
@@ -800,6 +813,7 @@ int hpmvs_engine_set_start_mode(hpmvs_engine_t* e, int mode) {
 int hpmvs_optimize_batch(hpmvs_engine_t* e, int n, const hpmvs_patch_t* in, hpmvs_patch_t* out, void* stream) {
     if (!e || n < 0 || (n > 0 && (!in || !out))) return HPMVS_E_ARG;
     if (n == 0) return 0;
+    HP_NVTX("hpmvs_optimize_batch (H2D + kernel + D2H)");
     std::lock_guard<std::mutex> lk(e->mu);
     HP_CUDA(cudaSetDevice(e->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
@@ -838,13 +852,14 @@ int hpmvs_optimize_batch(hpmvs_engine_t* e, int n, const hpmvs_patch_t* in, hpmv
 int hpmvs_optimize_batch_submit(hpmvs_engine_t* e, int n, const hpmvs_patch_t* in, hpmvs_patch_t* out, void* stream) {
     if (!e || !stream || n < 0 || (n > 0 && (!in || !out))) return HPMVS_E_ARG;
     if (n == 0) return 0;
+    HP_NVTX("hpmvs_optimize_batch_submit (enqueue H2D + kernel + D2H)");
     std::lock_guard<std::mutex> lk(e->mu);
     HP_CUDA(cudaSetDevice(e->device));
     cudaStream_t s = (cudaStream_t)stream;
     int rc = check_ready(e);
     if (rc) return rc;
     if (!valid_view_ids(e, n, in)) return HPMVS_E_ARG;
-    hpmvs_engine::Stage& st = e->stage2[e->submit_seq++ % 2];
+    hpmvs_engine::Stage& st = e->stage2[e->submit_seq++ % 8];
     if (!st.done) HP_CUDA(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
     if ((size_t)n > st.cap) {
         HP_CUDA(cudaEventSynchronize(st.done));
@@ -972,6 +987,7 @@ int hpmvs_depth_set_batch(hpmvs_engine_t* e, int n, const hpmvs_patch_t* patches
 int hpmvs_depth_unset_batch(hpmvs_engine_t* e, int n, const hpmvs_patch_t* patches, void* stream) { return depth_set_impl(e, n, patches, stream, 1); }
 static int depth_set_impl(hpmvs_engine_t* e, int n, const hpmvs_patch_t* patches, void* stream, int subtract) {
     if (!e || n < 0 || (n > 0 && !patches)) return HPMVS_E_ARG;
+    HP_NVTX("hpmvs_depth_set/unset_batch");
     if (n == 0) return 0;
     std::lock_guard<std::mutex> lk(e->mu);
     HP_CUDA(cudaSetDevice(e->device));
@@ -992,6 +1008,7 @@ static int depth_set_impl(hpmvs_engine_t* e, int n, const hpmvs_patch_t* patches
 
 int hpmvs_accept_batch(hpmvs_engine_t* e, int n, const hpmvs_patch_t* patches, float margin, int32_t* out, void* stream) {
     if (!e || n < 0 || (n > 0 && (!patches || !out))) return HPMVS_E_ARG;
+    HP_NVTX("hpmvs_accept_batch");
     if (n == 0) return 0;
     std::lock_guard<std::mutex> lk(e->mu);
     HP_CUDA(cudaSetDevice(e->device));
@@ -1018,6 +1035,106 @@ int hpmvs_accept_batch(hpmvs_engine_t* e, int n, const hpmvs_patch_t* patches, f
     return 0;
 }
 
+// Border de-duplication on device-resident records (the gathered patch set on the root rank): keep[i] = 1 for the survivors, *nkeep
+// their number (device int, may be NULL).  Asynchronous on `stream`.
+int hpmvs_dedup_border_device(hpmvs_engine_t* e, int n, const hpmvs_patch_t* d_records, const int32_t* d_owner, const double origin[3],
+                              double cell, uint8_t* d_keep, int32_t* d_nkeep, void* stream) {
+    if (!e || n < 0 || (n > 0 && (!d_records || !d_owner || !d_keep)) || !(cell > 0.0)) return HPMVS_E_ARG;
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(e->mu);
+    HP_CUDA(cudaSetDevice(e->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    size_t cap = 1024;
+    while (cap < (size_t)n * 2) cap <<= 1;
+    const size_t need = cap * (8 + 4 + 8 + 8) + (size_t)n * 4 + 64;
+    if (need > e->cap_dedup) {
+        if (e->d_dedup) cudaFree(e->d_dedup);
+        e->d_dedup = nullptr; e->cap_dedup = 0;
+        HP_CUDA(cudaMalloc(&e->d_dedup, need));
+        e->cap_dedup = need;
+    }
+    hp::DedupTable T;
+    unsigned char* p = e->d_dedup;
+    T.keys = (unsigned long long*)p; p += cap * 8;
+    T.best_score = (unsigned long long*)p; p += cap * 8;
+    T.best_who = (unsigned long long*)p; p += cap * 8;
+    T.best_nimg = (int*)p; p += cap * 4;
+    T.slot_of = (int*)p;
+    T.cap_mask = (unsigned)(cap - 1);
+    HP_CUDA(cudaMemsetAsync(T.keys, 0, cap * 8, s));
+    HP_CUDA(cudaMemsetAsync(T.best_score, 0xff, cap * 16, s));           // best_score and best_who: all ones = "no candidate yet"
+    HP_CUDA(cudaMemsetAsync(T.best_nimg, 0, cap * 4, s));
+    if (d_nkeep) HP_CUDA(cudaMemsetAsync(d_nkeep, 0, sizeof(int), s));
+    const double zero[3] = {0.0, 0.0, 0.0};
+    if (!origin) origin = zero;
+    int grid = (n + 255) / 256;
+    if (grid > e->sm_count * 8) grid = e->sm_count * 8;
+    hp::dedup_insert_kernel<<<grid, 256, 0, s>>>(d_records, n, origin[0], origin[1], origin[2], cell, T);
+    hp::dedup_score_kernel<<<grid, 256, 0, s>>>(d_records, n, T);
+    hp::dedup_who_kernel<<<grid, 256, 0, s>>>(d_records, d_owner, n, T);
+    int* nk = d_nkeep;
+    if (!nk) { nk = (int*)(e->d_dedup + need - 16); HP_CUDA(cudaMemsetAsync(nk, 0, sizeof(int), s)); }   // no counter wanted: count into a scratch word
+    hp::dedup_verdict_kernel<<<grid, 256, 0, s>>>(d_owner, n, T, d_keep, nk);
+    e->launches += 4;
+    HP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- device-resident forms of the steps around optimize() in a level of the loop: no host staging, asynchronous on `stream` -------
+int hpmvs_expand_candidates_device(hpmvs_engine_t* e, int n, const hpmvs_patch_t* d_parents, const float* d_widths, int mode,
+                                   hpmvs_patch_t* d_out, void* stream) {
+    if (!e || n < 0 || (n > 0 && (!d_parents || !d_widths || !d_out)) || (mode != 4 && mode != 6)) return HPMVS_E_ARG;
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(e->mu);
+    HP_CUDA(cudaSetDevice(e->device));
+    if (e->ncams <= 0) return HPMVS_E_STATE;
+    int rc = sync_cameras(e); if (rc) return rc;
+    hp::ExpandDirs D{};
+    for (int ii = 0; ii < mode; ii++) {                       // the host function's own angles and libm calls (host_scene.cpp)
+        const float angle = (mode == 6) ? (float)(2.0 * M_PI / mode * ii) : (float)(2.0 * M_PI / mode * ii + M_PI / 4);
+        D.dx[ii] = (float)cos((double)angle); D.dy[ii] = (float)sin((double)angle);
+    }
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    const int total = n * mode;
+    hp::expand_candidates_kernel<<<(total + 127) / 128, 128, 0, s>>>(e->d_cams, e->ncams, d_parents, d_widths, n, mode, D, d_out);
+    e->launches++;
+    HP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int hpmvs_depth_set_batch_device(hpmvs_engine_t* e, int n, const hpmvs_patch_t* d_patches, int subtract, void* stream) {
+    if (!e || n < 0 || (n > 0 && !d_patches)) return HPMVS_E_ARG;
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(e->mu);
+    HP_CUDA(cudaSetDevice(e->device));
+    int rc = ensure_depths(e); if (rc) return rc;
+    rc = sync_cameras(e); if (rc) return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    const hp::KParams K = make_params(e, d_patches, e->d_out, n);
+    const int total = n * HPMVS_MAX_VIEWS;
+    hp::depth_set_kernel<<<(total + 255) / 256, 256, 0, s>>>(K, d_patches, n, subtract ? 1 : 0);
+    e->launches++;
+    HP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int hpmvs_accept_batch_device(hpmvs_engine_t* e, int n, const hpmvs_patch_t* d_patches, float margin, int32_t* d_out, void* stream) {
+    if (!e || n < 0 || (n > 0 && (!d_patches || !d_out))) return HPMVS_E_ARG;
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(e->mu);
+    HP_CUDA(cudaSetDevice(e->device));
+    int rc = ensure_depths(e); if (rc) return rc;
+    rc = sync_cameras(e); if (rc) return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    const hp::KParams K = make_params(e, d_patches, e->d_out, n);
+    int grid = (n + 7) / 8;
+    if (grid > e->sm_count * 8) grid = e->sm_count * 8;
+    hp::accept_kernel<<<grid, 256, 0, s>>>(K, d_patches, n, margin, d_out);
+    e->launches++;
+    HP_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int hpmvs_engine_download_depth(hpmvs_engine_t* e, int cam, int level, float* out, int* rows, int* cols) {
     if (!e || cam < 0 || cam >= e->ncams || level < 0 || level > e->opt.maxlevel || !rows || !cols) return HPMVS_E_ARG;
     std::lock_guard<std::mutex> lk(e->mu);
@@ -1034,7 +1151,7 @@ int hpmvs_engine_dump_round_log(hpmvs_engine_t* e, const char* path) {
     std::lock_guard<std::mutex> lk(e->mu);
     HP_CUDA(cudaSetDevice(e->device));
     HP_CUDA(cudaDeviceSynchronize());
-    hpmvs_engine::WfContext& w = e->wfb[(e->wf_seq + 1) % 2].part[0];
+    hpmvs_engine::WfContext& w = e->wfb[(e->wf_seq + HP_WF_BATCHES - 1) % HP_WF_BATCHES].part[0];
     if (!w.round_log) return HPMVS_E_STATE;
     hp::WfCtl c;
     HP_CUDA(cudaMemcpy(&c, w.ctl, sizeof(c), cudaMemcpyDeviceToHost));

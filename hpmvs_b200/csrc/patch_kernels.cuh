@@ -1538,6 +1538,100 @@ __global__ void accept_kernel(const KParams K, const hpmvs_patch_t* __restrict__
 }
 
 // ----------------------------------------------------------------------------------------------------------
+// Candidate construction of CellProcessor::extend (mode 6, CellProcessor.cpp:98-119) and ::branch (mode 4, :227-249) on
+// device-resident parents: one thread per (parent, direction).  The direction cosines are formed on the HOST (cos / sin of six or four
+// constant angles with the caller's libm, exactly the values the host function hpmvs_expand_candidates uses) and passed in.
+// ----------------------------------------------------------------------------------------------------------
+struct ExpandDirs { float dx[6], dy[6]; };
+__global__ void expand_candidates_kernel(const DevCamera* __restrict__ cams, int ncams, const hpmvs_patch_t* __restrict__ parents,
+                                         const float* __restrict__ widths, int n, int mode, ExpandDirs D, hpmvs_patch_t* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * mode) return;
+    const int i = t / mode, ii = t - mode * i;
+    hpmvs_patch_t q = parents[i];
+    const int ref = (q.nimages > 0 && q.images[0] >= 0 && q.images[0] < ncams) ? q.images[0] : 0;
+    const DevCamera& rc = cams[ref];
+    const f3 nrm = f3{q.normal[0], q.normal[1], q.normal[2]};
+    const f3 ya = normalized3(cross3(nrm, f3{rc.xaxis[0], rc.xaxis[1], rc.xaxis[2]}));
+    const f3 xa = cross3(ya, nrm);
+    const float width = widths[i];
+    const float extend = (mode == 6) ? width : (float)((double)width / 4.0);
+    const float dx = D.dx[ii], dy = D.dy[ii];
+    q.center[0] = q.center[0] + (dx * xa.x + dy * ya.x) * extend;
+    q.center[1] = q.center[1] + (dx * xa.y + dy * ya.y) * extend;
+    q.center[2] = q.center[2] + (dx * xa.z + dy * ya.z) * extend;
+    q.scale = (mode == 6) ? (float)((double)width * 0.9 / 2.0) : (float)((double)width * 0.45 / 2.0);
+    out[t] = q;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Border de-duplication after the final multi-GPU gather (device form of hpmvs_dedup_border, host_pipeline.cpp): patches of DIFFERENT
+// ranks that fall into the same cubic cell are reduced to the best supported one - most views (CellProcessor::filter's spirit,
+// CellProcessor.cpp:43-82), then the lower final score, then the lower rank, then the lower index; patches of the winner's own rank
+// in that cell all stay.  Open-addressing hash table on the packed cell key, then three atomic reduction passes and a verdict pass.
+// ----------------------------------------------------------------------------------------------------------
+struct DedupTable {
+    unsigned long long* keys;        // [cap] packed cell key + 1 (0 = empty)
+    int* best_nimg;                  // [cap]
+    unsigned long long* best_score;  // [cap] order-preserving bits of the score
+    unsigned long long* best_who;    // [cap] (owner << 32) | index
+    int* slot_of;                    // [n]
+    unsigned cap_mask;
+};
+__device__ __forceinline__ unsigned long long dedup_key(const float* c, double ox, double oy, double oz, double cell) {
+    const long long off = 1ll << 20, hi = (1ll << 21) - 1;
+    long long k0 = (long long)floor(((double)c[0] - ox) / cell) + off, k1 = (long long)floor(((double)c[1] - oy) / cell) + off,
+              k2 = (long long)floor(((double)c[2] - oz) / cell) + off;
+    k0 = k0 < 0 ? 0 : (k0 > hi ? hi : k0); k1 = k1 < 0 ? 0 : (k1 > hi ? hi : k1); k2 = k2 < 0 ? 0 : (k2 > hi ? hi : k2);
+    return ((unsigned long long)k0 << 42) | ((unsigned long long)k1 << 21) | (unsigned long long)k2;
+}
+__device__ __forceinline__ unsigned long long ordered_bits(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__global__ void dedup_insert_kernel(const hpmvs_patch_t* __restrict__ rec, int n, double ox, double oy, double oz, double cell, DedupTable T) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int slot = -1;
+        if (rec[i].status == HPMVS_OK) {
+            const unsigned long long key = dedup_key(rec[i].center, ox, oy, oz, cell) + 1ull;
+            unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 32) & T.cap_mask;
+            for (;;) {
+                const unsigned long long prev = atomicCAS(&T.keys[h], 0ull, key);
+                if (prev == 0ull || prev == key) { slot = (int)h; break; }
+                h = (h + 1) & T.cap_mask;
+            }
+            atomicMax(&T.best_nimg[slot], rec[i].nimages);
+        }
+        T.slot_of[i] = slot;
+    }
+}
+__global__ void dedup_score_kernel(const hpmvs_patch_t* __restrict__ rec, int n, DedupTable T) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int slot = T.slot_of[i];
+        if (slot >= 0 && rec[i].nimages == T.best_nimg[slot]) atomicMin(&T.best_score[slot], ordered_bits(rec[i].score));
+    }
+}
+__global__ void dedup_who_kernel(const hpmvs_patch_t* __restrict__ rec, const int* __restrict__ owner, int n, DedupTable T) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int slot = T.slot_of[i];
+        if (slot >= 0 && rec[i].nimages == T.best_nimg[slot] && ordered_bits(rec[i].score) == T.best_score[slot])
+            atomicMin(&T.best_who[slot], ((unsigned long long)(unsigned)owner[i] << 32) | (unsigned)i);
+    }
+}
+__global__ void dedup_verdict_kernel(const int* __restrict__ owner, int n, DedupTable T, unsigned char* __restrict__ keep, int* __restrict__ nkeep) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int slot = T.slot_of[i];
+        unsigned char k = 0;
+        if (slot >= 0) {
+            const unsigned long long w = T.best_who[slot];
+            k = ((unsigned)(w & 0xffffffffull) == (unsigned)i || (int)(w >> 32) == owner[i]) ? 1 : 0;
+        }
+        keep[i] = k;
+        if (k) atomicAdd(nkeep, 1);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
 // image layout kernels
 // ----------------------------------------------------------------------------------------------------------
 // interleaved RGB (tightly packed staging copy) -> pitched RGBX

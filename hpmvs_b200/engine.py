@@ -86,6 +86,10 @@ def _lib():
         L.hpmvs_depth_set_batch.argtypes = [vp, C.c_int, vp, vp]
         L.hpmvs_depth_unset_batch.argtypes = [vp, C.c_int, vp, vp]
         L.hpmvs_accept_batch.argtypes = [vp, C.c_int, vp, C.c_float, ip, vp]
+        L.hpmvs_expand_candidates_device.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp]
+        L.hpmvs_depth_set_batch_device.argtypes = [vp, C.c_int, vp, C.c_int, vp]
+        L.hpmvs_accept_batch_device.argtypes = [vp, C.c_int, vp, C.c_float, vp, vp]
+        L.hpmvs_dedup_border_device.argtypes = [vp, C.c_int, vp, vp, dp, C.c_double, vp, vp, vp]
         L.hpmvs_engine_download_depth.argtypes = [vp, C.c_int, C.c_int, fp, ip, ip]
         L.hpmvs_expand_candidates.argtypes = [C.c_int, C.POINTER(Camera), C.c_int, vp, fp, C.c_int, vp]
         L.hpmvs_seed_patches.argtypes = [C.POINTER(Options), C.c_int, C.POINTER(Camera), C.c_int, dp, ip, ip, vp, u8p]
@@ -225,6 +229,23 @@ class Engine:
         e.set_covis(extract_covis(len(cams), scene.meas_offsets, scene.meas_cam, compat_covis))
         return e
 
+    @classmethod
+    def from_stream(cls, scene_fn, options: Optional[Options] = None, device: int = 0, compat_covis: bool = True):
+        """Resident scene from a generator that streams its views: scene_fn(image_sink) must call image_sink(i, nvm_cameras, image)
+        once per view (in order) and return the SynthScene (without images).  Each view is uploaded and its pyramid built as it
+        arrives, so the host never holds more than one level-0 image.  Returns (engine, scene)."""
+        e = cls(options, device)
+        ml = e.options.maxlevel
+
+        def sink(i, nvm_cams, img):
+            if i == 0:
+                e.set_cameras([camera_from_nvm(c.f, c.q, c.c, c.width, c.height, ml) for c in nvm_cams])
+            e.upload_image(i, 0, img)
+            e.build_pyramid(i)
+        scene = scene_fn(sink)
+        e.set_covis(extract_covis(len(scene.cameras), scene.meas_offsets, scene.meas_cam, compat_covis))
+        return e, scene
+
     # -- the hot path -----------------------------------------------------------------------
     def optimize(self, patches: np.ndarray, out: Optional[np.ndarray] = None, stream: int = 0) -> np.ndarray:
         """n x PatchOptimizer::optimize(Patch3d&): host records in, host records out (H2D + kernel + D2H)."""
@@ -293,6 +314,22 @@ class Engine:
         out = np.zeros((len(patches), 3), np.int32)
         _check(_lib().hpmvs_accept_batch(self._h, len(patches), patches.ctypes.data, float(margin), _p(out, C.c_int32), None))
         return out
+
+    def expand_candidates_device(self, n: int, d_parents: int, d_widths: int, mode: int, d_out: int, stream: int = 0) -> None:
+        """Candidates of CellProcessor::extend (mode 6) / ::branch (mode 4) for n device-resident parents -> mode*n device records."""
+        _check(_lib().hpmvs_expand_candidates_device(self._h, int(n), d_parents, d_widths, int(mode), d_out, stream or None))
+
+    def depth_set_device(self, n: int, d_patches: int, subtract: bool = False, stream: int = 0) -> None:
+        _check(_lib().hpmvs_depth_set_batch_device(self._h, int(n), d_patches, 1 if subtract else 0, stream or None))
+
+    def accept_device(self, n: int, d_patches: int, margin: float, d_out: int, stream: int = 0) -> None:
+        _check(_lib().hpmvs_accept_batch_device(self._h, int(n), d_patches, float(margin), d_out, stream or None))
+
+    def dedup_border_device(self, n: int, d_records: int, d_owner: int, origin, cell: float, d_keep: int, d_nkeep: int = 0, stream: int = 0) -> None:
+        """hpmvs_dedup_border_device: border de-duplication of n device-resident records (owner = int32 rank per record); d_keep receives
+        n uint8 flags, d_nkeep (optional device int32) the number of survivors.  Asynchronous on `stream`."""
+        org = np.ascontiguousarray(origin if origin is not None else (0.0, 0.0, 0.0), np.float64)
+        _check(_lib().hpmvs_dedup_border_device(self._h, int(n), d_records, d_owner, _p(org, C.c_double), float(cell), d_keep, d_nkeep or None, stream or None))
 
     def download_depth(self, cam: int, level: int) -> np.ndarray:
         r, c = C.c_int32(), C.c_int32()

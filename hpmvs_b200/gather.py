@@ -85,6 +85,43 @@ def gather_to_root(records: np.ndarray, device: Optional[torch.device] = None, r
     return host, owner
 
 
+STATUS_WORD = PATCH_DTYPE.fields["status"][1] // 4      # int32 index of hpmvs_patch_t.status inside a record
+
+
+def gather_to_root_device(d_records: torch.Tensor, root: int = 0):
+    """Device-resident form of gather_to_root: `d_records` is a uint8 [n, 208] tensor on this rank's GPU (NCCL) - the accepted records
+    of this rank; the root receives every rank's slice straight into one device tensor (no host staging, no padding).
+    Returns (records uint8 [total, 208], owner int32 [total]) on the root, (None, None) elsewhere."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return d_records, torch.zeros(len(d_records), dtype=torch.int32, device=d_records.device)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = d_records.device
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, torch.tensor([len(d_records)], dtype=torch.int64, device=dev))
+    counts = counts.cpu().tolist()
+    if rank != root:
+        if len(d_records):
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, d_records.contiguous(), root)]):
+                w.wait()
+        return None, None
+    total = int(sum(counts))
+    out = torch.empty((total, REC), dtype=torch.uint8, device=dev)
+    offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    ops = []
+    for r in range(world):
+        if counts[r] == 0:
+            continue
+        if r == root:
+            out[offs[r]:offs[r + 1]] = d_records
+        else:
+            ops.append(dist.P2POp(dist.irecv, out[offs[r]:offs[r + 1]], r))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    owner = torch.repeat_interleave(torch.arange(world, dtype=torch.int32, device=dev), torch.tensor(counts, device=dev))
+    return out, owner
+
+
 def root_cube(patches: np.ndarray):
     """hpmvs_root_cube: the octree's root cube as Scene::initPatches forms it (Scene.cpp:186-193) -> (origin[3], width)."""
     import ctypes as C

@@ -43,6 +43,7 @@ class EngineBackend:
     def optimize(self, rec): return self.e.optimize(np.ascontiguousarray(rec))
     def accept(self, rec, margin): return self.e.accept(np.ascontiguousarray(rec), margin)
     def depth_set(self, rec): self.e.depth_set(np.ascontiguousarray(rec))
+    def depth_unset(self, rec): self.e.depth_unset(np.ascontiguousarray(rec))
     def expand(self, parents, widths, mode): return self._expand(self.e.cameras, np.ascontiguousarray(parents), widths, mode)
 
 
@@ -66,7 +67,8 @@ def _pack(keys: np.ndarray) -> np.ndarray:
 
 class WavefrontDriver:
     def __init__(self, backend, origin, root_width: float, start_level: int, final_level: int, max_rounds: int = 64,
-                 final_min_level: int = 9, cameras=None, shard_count: int = 1, shard_rank: int = 0, shard_level: int = 0):
+                 final_min_level: int = 9, cameras=None, shard_count: int = 1, shard_rank: int = 0, shard_level: int = 0,
+                 minlevel: int = 0, level_cameras=None):
         # final_min_level = HpmvsOptions::PATCH_FINAL_MINLEVEL as the CLI sets it (src/main.cpp:44,234): a cell below that tree
         # level whose patch yields no child when it branches is split anyway and loses its patch (CellProcessor.cpp:266-283)
         self.final_min_level = final_min_level
@@ -77,6 +79,13 @@ class WavefrontDriver:
         if cameras is not None:
             self.P0 = np.stack([np.ctypeslib.as_array(c.P)[0].astype(np.float64) for c in cameras])     # [ncams, 3, 4]
             self.k00 = np.array([c.k00 for c in cameras], np.float64)
+        # level support (Scene::getLevelSupport, Scene.cpp:335-344) needs the camera centres and k00 + k11
+        lc = level_cameras if level_cameras is not None else cameras
+        self.minlevel = minlevel
+        self.cam_center = None
+        if lc is not None:
+            self.cam_center = np.stack([np.ctypeslib.as_array(c.center).astype(np.float32) for c in lc])
+            self.cam_ksum = np.array([np.float32(c.k00) + np.float32(c.k11) for c in lc], np.float32)
         self.b = backend
         self.origin = np.asarray(origin, np.float64)
         self.root_width = float(root_width)
@@ -95,17 +104,80 @@ class WavefrontDriver:
         self.stats.optimized_ok += int((out["status"] == 0).sum())
         return out
 
-    def _insert(self, level_cells: Dict[int, np.ndarray], rec: np.ndarray, width: float) -> np.ndarray:
-        """One patch per cell; on a collision the patch with more views wins (filter), then the earlier one.
-        Returns a mask of the records that now live in the grid."""
-        keys = _pack(_cell_keys(rec["center"], self.origin, width))
+    @staticmethod
+    def _filter_pick(members) -> int:
+        """CellProcessor::filter (CellProcessor.cpp:43-82): keep the patch with the smallest mean signed distance of the OTHERS' centres
+        along its own normal; first minimum in arrival order.  f32, same operation order as host_pipeline.cpp."""
+        f = np.float32
+        best, bestd = 0, f(3.402823466e+38)
+        for a, A in enumerate(members):
+            n = A["normal"][:3].astype(np.float32).copy()
+            z = f(f(n[0] * n[0] + n[1] * n[1]) + n[2] * n[2])
+            if z > 0:
+                n = n / np.sqrt(z, dtype=np.float32)
+            dist = f(0)
+            for b, B in enumerate(members):
+                if a == b:
+                    continue
+                d = (B["center"][:3] - A["center"][:3]).astype(np.float32)
+                dist = f(dist + f(f(n[0] * d[0] + n[1] * d[1]) + n[2] * d[2]))
+            dist = f(dist / f(len(members) - 1))
+            if dist < bestd:
+                best, bestd = a, dist
+        return best
+
+    def _insert(self, level_cells: Dict[int, np.ndarray], rec: np.ndarray, width: float):
+        """One patch per cell; patches that share a cell go through CellProcessor::filter's rule.  Returns (mask of the records that
+        now live in the grid, list of resident patches that lost their cell - their depths must be subtracted)."""
+        keys = _pack(_cell_keys(rec["center"], self.origin, width)).tolist()
         live = np.zeros(len(rec), bool)
-        for i, k in enumerate(keys.tolist()):
+        removed = []
+        groups: Dict[int, List[int]] = {}
+        for i, k in enumerate(keys):
+            groups.setdefault(k, []).append(i)
+        for k, g in groups.items():                                   # dicts keep first-appearance order, like the C++ `order` list
             old = level_cells.get(k)
-            if old is None or rec["nimages"][i] > old["nimages"]:
-                level_cells[k] = rec[i].copy()
-                live[i] = True
-        return live
+            members = ([old] if old is not None else []) + [rec[i] for i in g]
+            b = self._filter_pick(members) if len(members) > 1 else 0
+            if old is not None:
+                if b == 0:
+                    continue
+                removed.append(old)
+                level_cells[k] = rec[g[b - 1]].copy()
+                live[g[b - 1]] = True
+            else:
+                level_cells[k] = rec[g[b]].copy()
+                live[g[b]] = True
+        return live, removed
+
+    def _level_support(self, rec: np.ndarray) -> np.ndarray:
+        """Scene::getLevelSupport(patch, MINLEVEL): views whose rounded pyramid level for this patch is above MINLEVEL (f32 / f64 mix
+        of Camera::getLevel, Camera.cpp:92-95, as host_pipeline.cpp::host_level)."""
+        out = np.zeros(len(rec), np.int64)
+        if self.cam_center is None:
+            return out + 1
+        f = np.float32
+        for i in range(len(rec)):
+            c = rec["center"][i].astype(np.float32)
+            for k in range(int(rec["nimages"][i])):
+                cam = int(rec["images"][i, k])
+                d = (c - self.cam_center[cam]).astype(np.float32)
+                p = (d * d).astype(np.float32)
+                fz = np.sqrt(f(f(p[0] + p[2]) + f(p[1] + p[3])), dtype=np.float32)
+                lvl = f(np.log2(np.float64(f(rec["scale"][i] * self.cam_ksum[cam])) / (2.0 * np.float64(fz))))
+                r = int(np.floor(abs(float(lvl)) + 0.5)) * (1 if lvl >= 0 else -1)         # std::round: half away from zero
+                out[i] += r > self.minlevel
+        return out
+
+    def _commit(self, cells, rec, width):
+        """Insert the accepted records, subtract the depths of the residents they displace, set the depths of the new residents."""
+        live, removed = self._insert(cells, rec, width)
+        if removed:
+            self.b.depth_unset(np.array(removed, dtype=self.b.dtype))
+        fresh = rec[live]
+        if len(fresh):
+            self.b.depth_set(fresh)
+        return fresh
 
     def _mine(self, centers: np.ndarray) -> np.ndarray:
         if self.shard_count <= 1:
@@ -143,8 +215,7 @@ class WavefrontDriver:
         cells: Dict[int, np.ndarray] = {}
         level = self.start_level
         first = out[ok]
-        self._insert(cells, first, self.width(level))
-        self.b.depth_set(np.array(list(cells.values()), dtype=self.b.dtype) if cells else first[:0])
+        self._commit(cells, first, self.width(level))
         final: List[np.ndarray] = []
         while True:
             w = self.width(level)
@@ -184,9 +255,7 @@ class WavefrontDriver:
                 acc = acc[self._first_per_ref_pixel(acc, w)]
                 if len(acc) == 0:
                     break
-                live = self._insert(cells, acc, w)
-                new = acc[live]
-                self.b.depth_set(new)
+                new = self._commit(cells, acc, w)
                 n_ext += len(new)
                 frontier = new
             patches = np.array(list(cells.values()), dtype=self.b.dtype) if cells else first[:0]
@@ -194,10 +263,17 @@ class WavefrontDriver:
                 final.append(patches)
                 self.stats.per_level.append((level, n_ext, 0))
                 break
-            # branch into the next level: 4 candidates per patch, kept when they stay inside the parent's cell
-            cand = self.b.expand(patches, np.full(len(patches), w, np.float32), 4)
-            parent = np.repeat(np.arange(len(patches)), 4)
-            pkeys = _pack(_cell_keys(patches["center"], self.origin, w))[parent]
+            # branch into the next level (CellProcessor::branch).  A patch without level support is exhausted (CellProcessor.cpp:222-225):
+            # its cell keeps it and it is a final result at whatever level
+            exhausted = self._level_support(patches) < 1
+            if exhausted.any():
+                final.append(patches[exhausted])
+            pidx = np.nonzero(~exhausted)[0]
+            parents = patches[pidx]
+            # 4 candidates per patch, kept when they stay inside the parent's cell
+            cand = self.b.expand(parents, np.full(len(parents), w, np.float32), 4) if len(parents) else patches[:0]
+            parent = pidx[np.repeat(np.arange(len(parents)), 4)]
+            pkeys = _pack(_cell_keys(patches["center"], self.origin, w))[parent] if len(parents) else np.zeros(0, np.int64)
             inside = _pack(_cell_keys(cand["center"], self.origin, w)) == pkeys
             cand, parent, pkeys = cand[inside], parent[inside], pkeys[inside]
             res = self._optimize(cand) if len(cand) else cand
@@ -205,22 +281,46 @@ class WavefrontDriver:
             children = res[keep]
             branched_parents = np.unique(parent[keep]) if len(cand) else np.zeros(0, np.int64)
             # cells that did not branch keep their patch as a final result - from PATCH_FINAL_MINLEVEL on (CellProcessor.cpp:266-269)
-            stay = np.ones(len(patches), bool); stay[branched_parents] = False
+            stay = ~exhausted; stay[branched_parents] = False
+            gone = ~exhausted
             if level >= self.final_min_level:
                 final.append(patches[stay])
+                gone &= ~stay
+            # every other cell is split and its patch leaves the tree: Scene::setDepths(old, true) (CellProcessor.cpp:271-279)
+            if gone.any():
+                self.b.depth_unset(patches[gone])
             self.stats.per_level.append((level, n_ext, int(len(children))))
             cells = {}
             level += 1
-            self._insert(cells, children, self.width(level))
-            self.b.depth_set(np.array(list(cells.values()), dtype=self.b.dtype) if cells else children[:0])
+            self._commit(cells, children, self.width(level))
         return np.concatenate(final) if final else seeds[:0]
 
 
 # ----------------------------------------------------------------------------------------------------------------------
 # The same driver in C++ behind the C ABI (hpmvs_pipeline_run, hpmvs_b200/csrc/host_pipeline.cpp): the product's host path.
 # ----------------------------------------------------------------------------------------------------------------------
+EXCHANGE_FN = None
+
+
+def shard_subtrees(patches: np.ndarray, origin, root_width: float, min_subtrees: int, nranks: int):
+    """hpmvs_shard_subtrees: the reference's sub-tree split (getSubTrees, src/main.cpp:50-96) of a patch set as a table
+    (level[], key[n,3], rank[]) for run_native(subtrees=...)."""
+    import ctypes as C
+    from . import engine as E
+    L = E._lib()
+    p = np.ascontiguousarray(patches); org = np.ascontiguousarray(origin, np.float64)
+    cap = 4096
+    lvl = np.zeros(cap, np.int32); key = np.zeros((cap, 3), np.int64); rk = np.zeros(cap, np.int32)
+    L.hpmvs_shard_subtrees.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    m = L.hpmvs_shard_subtrees(len(p), p.ctypes.data, org.ctypes.data, float(root_width), int(min_subtrees), int(nranks), cap,
+                               lvl.ctypes.data, key.ctypes.data, rk.ctypes.data)
+    E._check(m)
+    return lvl[:m].copy(), key[:m].copy(), rk[:m].copy()
+
+
 def run_native(engine, seeds: np.ndarray, origin, root_width: float, start_level: int, final_level: int, final_min_level: int = 9,
-               max_rounds: int = 64, dedup_ref_pixel: bool = True, shard_count: int = 1, shard_rank: int = 0, shard_level: int = 0):
+               max_rounds: int = 64, dedup_ref_pixel: bool = True, shard_count: int = 1, shard_rank: int = 0, shard_level: int = 0,
+               minlevel: int = 0, subtrees=None, exchange=None):
     """Runs hpmvs_pipeline_run on `engine`; returns (final patch records, PipelineStats).  shard_count > 1: only the cells of tree
     level shard_level that are dealt to shard_rank are grown (one call per GPU; merge with gather.gather_patches + dedup_border)."""
     import ctypes as C
@@ -230,15 +330,47 @@ def run_native(engine, seeds: np.ndarray, origin, root_width: float, start_level
     class Params(C.Structure):
         _fields_ = [("origin", C.c_double * 3), ("root_width", C.c_double), ("start_level", C.c_int32), ("final_level", C.c_int32),
                     ("final_min_level", C.c_int32), ("max_rounds", C.c_int32), ("dedup_ref_pixel", C.c_int32), ("ncams", C.c_int32),
-                    ("cams", C.POINTER(E.Camera)), ("shard_count", C.c_int32), ("shard_rank", C.c_int32), ("shard_level", C.c_int32)]
+                    ("cams", C.POINTER(E.Camera)), ("shard_count", C.c_int32), ("shard_rank", C.c_int32), ("shard_level", C.c_int32),
+                    ("minlevel", C.c_int32), ("nsub", C.c_int32), ("sub_level", C.c_void_p), ("sub_key", C.c_void_p), ("sub_rank", C.c_void_p),
+                    ("exchange", C.c_void_p), ("exchange_user", C.c_void_p)]
 
     class Stats(C.Structure):
         _fields_ = [("optimize_calls", C.c_int64), ("optimized_ok", C.c_int64), ("seconds_optimize", C.c_double), ("seconds_accept", C.c_double),
-                    ("nlevels", C.c_int32), ("level", C.c_int32 * 24), ("extended", C.c_int64 * 24), ("branched", C.c_int64 * 24)]
+                    ("nlevels", C.c_int32), ("level", C.c_int32 * 24), ("extended", C.c_int64 * 24), ("branched", C.c_int64 * 24),
+                    ("exchanged", C.c_int64)]
 
     cams = (E.Camera * len(engine.cameras))(*engine.cameras)
+    keep_alive = []
+    nsub, p_lvl, p_key, p_rk = 0, None, None, None
+    if subtrees is not None:
+        lvl, key, rk = (np.ascontiguousarray(subtrees[0], np.int32), np.ascontiguousarray(subtrees[1], np.int64), np.ascontiguousarray(subtrees[2], np.int32))
+        keep_alive += [lvl, key, rk]
+        nsub, p_lvl, p_key, p_rk = len(lvl), lvl.ctypes.data, key.ctypes.data, rk.ctypes.data
+    cb = None
+    recv_bufs = []
+    if exchange is not None:
+        # exchange(records) -> all ranks' records concatenated in rank order (every rank calls it the same number of times)
+        CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int))
+
+        def _cb(user, n_send, send, recv, n_recv):
+            try:
+                mine = np.frombuffer((C.c_char * (n_send * E.PATCH_DTYPE.itemsize)).from_address(send), dtype=E.PATCH_DTYPE, count=n_send).copy() \
+                    if n_send else np.zeros(0, E.PATCH_DTYPE)
+                allr = np.ascontiguousarray(exchange(mine))
+                recv_bufs.append(allr)                             # valid until the next call
+                del recv_bufs[:-2]
+                recv[0] = allr.ctypes.data
+                n_recv[0] = len(allr)
+                return 0
+            except Exception:                                      # never let an exception cross the C boundary
+                import traceback
+                traceback.print_exc()
+                return -1
+        cb = CB(_cb)
+        keep_alive.append(cb)
     prm = Params((C.c_double * 3)(*[float(v) for v in origin]), float(root_width), start_level, final_level, final_min_level, max_rounds,
-                 1 if dedup_ref_pixel else 0, len(engine.cameras), cams, shard_count, shard_rank, shard_level)
+                 1 if dedup_ref_pixel else 0, len(engine.cameras), cams, shard_count, shard_rank, shard_level, minlevel,
+                 nsub, p_lvl, p_key, p_rk, C.cast(cb, C.c_void_p) if cb is not None else None, None)
     st = Stats()
     s = np.ascontiguousarray(seeds)
     assert s.dtype == E.PATCH_DTYPE

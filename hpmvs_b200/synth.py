@@ -365,7 +365,7 @@ def box_quads(center, size, seed: int, tex_size: int = 512) -> List[Quad]:
 
 def city_scene(n_views: int = 100, width: int = 1920, height: int = 1080, focal: float = 1500.0,
                n_boxes: int = 8, n_seeds: int = 100000, seed: int = 4, loop_radius: float = 14.0,
-               max_meas: int = 11, name: Optional[str] = None) -> SynthScene:
+               max_meas: int = 11, name: Optional[str] = None, image_sink=None) -> SynthScene:
     """BASELINE config 4/5 family: cameras on a loop around a block of textured boxes standing on a
     textured ground plane; seeds sampled on the faces (with depth noise) and measured in up to
     `max_meas` consecutive views that see them un-occluded-ish (front-facing test only)."""
@@ -386,7 +386,14 @@ def city_scene(n_views: int = 100, width: int = 1920, height: int = 1080, focal:
         c = np.array([loop_radius * math.cos(a), -2.0 - 1.0 * math.sin(3 * a), loop_radius * math.sin(a)])
         R = look_at(c, (0.0, -1.5, 0.0), up=(0.0, -1.0, 0.0))
         cams.append(NVMCamera(f"view{i:04d}.ppm", focal, quat_from_rotation(R), c, 0.0, width, height))
-    images = [render(c, quads) for c in cams]
+    if image_sink is None:
+        images = [render(c, quads) for c in cams]
+    else:
+        # streaming form for scenes whose level-0 pixels do not fit host memory (500 views x 4K = 12 GB): every view is rendered,
+        # handed to image_sink(index, cameras, image) - which uploads it - and dropped; the returned scene carries no images
+        images = []
+        for i, c in enumerate(cams):
+            image_sink(i, cams, render(c, quads))
     # seeds on box side faces + ground, area-weighted
     areas = np.array([np.linalg.norm(np.cross(q.eu, q.ev)) for q in quads])
     areas[0] *= 0.15

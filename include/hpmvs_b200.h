@@ -196,6 +196,15 @@ int  hpmvs_engine_download_depth(hpmvs_engine_t *e, int cam, int level, float *o
 int  hpmvs_expand_candidates(int ncams, const hpmvs_camera_t *cams, int n, const hpmvs_patch_t *parents,
                              const float *widths, int mode, hpmvs_patch_t *out);
 
+/* Device-resident forms of the three steps above (records, widths and results live in HBM; no host staging; asynchronous on `stream`):
+ * a level of the loop can chain candidates -> hpmvs_optimize_batch_device -> acceptance counts -> depth updates without the patch
+ * records crossing PCIe; only the per-patch verdicts (3 ints) and the cell bookkeeping need the host.  View ids in device-resident
+ * records are the caller's responsibility (the host-buffer calls validate them). */
+int  hpmvs_expand_candidates_device(hpmvs_engine_t *e, int n, const hpmvs_patch_t *d_parents, const float *d_widths, int mode,
+                                    hpmvs_patch_t *d_out, void *stream);
+int  hpmvs_depth_set_batch_device(hpmvs_engine_t *e, int n, const hpmvs_patch_t *d_patches, int subtract, void *stream);
+int  hpmvs_accept_batch_device(hpmvs_engine_t *e, int n, const hpmvs_patch_t *d_patches, float margin, int32_t *d_out, void *stream);
+
 /* ---- the loop around the path: level-synchronous expand -> optimize -> filter driver (host C++, hpmvs_b200/csrc/host_pipeline.cpp) ----
  * Batching stand-in for the reference's scheduler (CellProcessor::processQueue + DynOctTree, src/main.cpp:145-155): per octree level
  * all candidates of all cells go through ONE hpmvs_optimize_batch / hpmvs_accept_batch.  See the file header for what is kept. */
@@ -246,6 +255,11 @@ void hpmvs_free(void *p);
  * (the octree's low corner; NULL = world origin); keep[] receives the surviving
  * indices in ascending order (capacity n), the return value is their number. */
 int  hpmvs_dedup_border(int n, const hpmvs_patch_t *records, const int32_t *owner, const double origin[3], double cell, int32_t *keep);
+/* The same de-duplication on device-resident records (the gathered set on the root rank, straight out of the NCCL receive buffer):
+ * d_keep[i] = 1 for the survivors, *d_nkeep (device int, may be NULL) their number.  Four small kernels (hash insert on the packed cell
+ * key, then atomic reductions); asynchronous on `stream`. */
+int  hpmvs_dedup_border_device(hpmvs_engine_t *e, int n, const hpmvs_patch_t *d_records, const int32_t *d_owner, const double origin[3],
+                               double cell, uint8_t *d_keep, int32_t *d_nkeep, void *stream);
 /* Root cube of the patch octree as Scene::initPatches forms it (src/hpmvs/Scene.cpp:186-193): f32 bounding box of the centres, edge =
  * largest extent, centred on the box; origin = its low corner. */
 int  hpmvs_root_cube(int n, const hpmvs_patch_t *patches, double origin[3], double *width);

@@ -28,8 +28,20 @@ ok = (pre["status"] == 0) & ~(np.linalg.norm(pre["center"][:, :3] - seeds["cente
 c = pre["center"][ok][:, :3].astype(np.float64)
 mn, mx = c.min(0), c.max(0)
 width = float((mx - mn).max()); origin = (mn + mx) / 2.0 - width / 2.0
-first, last, shard_level = 5, 8, 3                                                # 512 level-3 cells dealt out to the ranks
+first, last = 5, 8
 args = dict(origin=origin, root_width=width, start_level=first, final_level=last)
+# the reference's sub-tree split over the seed points (getSubTrees, src/main.cpp:50-96), sub-trees dealt to the ranks
+sub = pipeline.shard_subtrees(seeds, origin, width, max(100, 16 * world), world)
+_, rk, nsub = gather.shard_cells(seeds, origin, width, max(100, 16 * world), world)
+my_seeds = np.ascontiguousarray(seeds[rk == rank]) if world > 1 else seeds
+exchanges = [0, 0.0]
+
+
+def exchange(mine):                                   # per-step border hand-off: every rank gets every rank's accepted records
+    t = time.perf_counter()
+    allr, _ = gather.gather_patches(mine)
+    exchanges[0] += 1; exchanges[1] += time.perf_counter() - t
+    return allr
 
 
 def quality(r):
@@ -40,11 +52,14 @@ torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 t0 = time.perf_counter()
-mine, st = pipeline.run_native(eng, seeds, shard_count=world, shard_rank=rank, shard_level=shard_level, **args)
+mine, st = pipeline.run_native(eng, my_seeds, shard_count=world, shard_rank=rank, subtrees=sub if world > 1 else None,
+                               exchange=exchange if world > 1 else None, **args)
 t_shard = time.perf_counter() - t0
-allr, owner = gather.gather_patches(mine)
-keep = gather.dedup_border(allr, owner, cell=width / (1 << last))
-merged = allr[keep]
+allr, owner = gather.gather_to_root(mine)
+merged = None
+if rank == 0:
+    keep = gather.dedup_border(allr, owner, cell=width / (1 << last), origin=origin)
+    merged = allr[keep]
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
@@ -60,7 +75,8 @@ if rank == 0:
     w = width / (1 << last)
     key = lambda r: set(map(tuple, np.floor((r["center"][:, :3].astype(np.float64) - origin) / w).astype(np.int64).tolist()))
     ka, kb = key(single), key(merged)
-    print(json.dumps({"workload": f"8-view 1280x960 synthetic plane, {n_seeds} NVM points, tree levels {first}..{last}, level-{shard_level} cells dealt to {world} GPUs",
+    print(json.dumps({"workload": f"8-view 1280x960 synthetic plane, {n_seeds} NVM points, tree levels {first}..{last}, {nsub} sub-trees dealt to {world} GPUs, per-step NCCL exchange",
+                      "exchange_calls": exchanges[0], "exchange_seconds_rank0": exchanges[1], "optimize_calls_rank0": int(st.optimized_calls),
                       "n_gpus": world, "sharded": dict(seconds_slowest_rank_pipeline=float(tt[0]), seconds_incl_gather_dedup=float(tt[1]),
                                                         gathered=int(len(allr)), **quality(merged)),
                       "single_gpu": dict(seconds=t_single, **quality(single)),

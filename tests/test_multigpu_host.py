@@ -160,3 +160,29 @@ def test_bench_shards_are_disjoint_and_deterministic():
     assert bench.bench_config("city100", "d", 44000, 100, 4) == bench.bench_config("city100", "d", 44000, 100, 4)
     assert np.array_equal(a.points, a2.points) and not np.array_equal(a.points, b.points)
     assert all(np.array_equal(x, y) for x, y in zip(a.images, b.images))   # the scene is replicated, seeds are sharded
+
+
+@pytest.mark.gpu
+def test_device_dedup_equals_host_dedup():
+    """hpmvs_dedup_border_device (hash insert + atomic reductions on the GPU) against the host function on the same gathered records:
+    same survivors, incl. ties on the view count (-> score, then rank decide), rejected records and a non-zero grid origin."""
+    rng = np.random.default_rng(11)
+    eng = hp.Engine()
+    for trial in range(5):
+        parts = [_make(int(rng.integers(1, 3000)), r, rng) for r in range(4)]
+        allr = np.concatenate(parts)
+        owner = np.concatenate([np.full(len(p), r, np.int32) for r, p in enumerate(parts)])
+        allr["status"][rng.random(len(allr)) < 0.1] = 2
+        allr["nimages"][rng.random(len(allr)) < 0.5] = 5
+        allr["score"][rng.random(len(allr)) < 0.3] = 0.05              # ties on the score as well -> rank, then index
+        cell = [0.5, 0.2, 0.05, 1.5, 0.01][trial]
+        origin = np.array([-1.03, -0.97, -1.01]) if trial % 2 else None
+        want = gather.dedup_border(allr, owner, cell, origin=origin)
+        d_rec = torch.from_numpy(allr.view(np.uint8).reshape(len(allr), -1).copy()).cuda()
+        d_own = torch.from_numpy(owner).cuda()
+        keep = torch.zeros(len(allr), dtype=torch.uint8, device="cuda"); nk = torch.zeros(1, dtype=torch.int32, device="cuda")
+        eng.dedup_border_device(len(allr), d_rec.data_ptr(), d_own.data_ptr(), origin, cell, keep.data_ptr(), nk.data_ptr())
+        torch.cuda.synchronize()
+        got = np.nonzero(keep.cpu().numpy())[0]
+        assert got.tolist() == want.tolist(), trial
+        assert int(nk.item()) == len(want)

@@ -95,3 +95,53 @@ def test_gpu_undistort_matches_the_host_twin(r):
     # r == 0 is a plain upload
     eng.upload_image_undistort(0, img, 600.0, 0.0)
     assert np.array_equal(eng.download_image(0, 0), img)
+
+
+@pytest.mark.gpu
+def test_device_resident_level_steps_equal_the_host_buffer_calls():
+    """One level of the loop chained on the device - candidates (kernel) -> optimize -> acceptance counts -> depth set / unset - with
+    records that never leave HBM must give the same bytes as the host-buffer entry points (which are pinned to the oracle and the
+    reference build above)."""
+    import torch
+    sc, orc, seeds = small_plane()
+    eng = hp.Engine.from_synth(sc)
+    parents = eng.optimize(to_engine(seeds))
+    parents = np.ascontiguousarray(parents[parents["status"] == 0][:150])
+    n = len(parents)
+    widths = np.linspace(0.05, 0.4, n).astype(np.float32)
+    up = lambda a: torch.from_numpy(a.view(np.uint8).reshape(len(a), -1).copy()).cuda()
+    d_par, d_w = up(parents), torch.from_numpy(widths).cuda()
+    for mode in (6, 4):
+        want = hp.expand_candidates(eng.cameras, parents, widths, mode)
+        d_c = torch.zeros((n * mode, hp.PATCH_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
+        eng.expand_candidates_device(n, d_par.data_ptr(), d_w.data_ptr(), mode, d_c.data_ptr())
+        torch.cuda.synchronize()
+        assert d_c.cpu().numpy().tobytes() == want.tobytes(), mode
+        # optimize the candidates where they are, then the acceptance counts where they are
+        d_o = torch.zeros_like(d_c)
+        eng.optimize_device(n * mode, d_c.data_ptr(), d_o.data_ptr())
+        torch.cuda.synchronize()
+        got = d_o.cpu().numpy().view(hp.PATCH_DTYPE).reshape(-1)
+        assert got.tobytes() == eng.optimize(want).tobytes()
+        eng.depth_reset()
+        eng.depth_set(parents)
+        d_cnt = torch.zeros((n * mode, 3), dtype=torch.int32, device="cuda")
+        eng.accept_device(n * mode, d_o.data_ptr(), 1.0, d_cnt.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(d_cnt.cpu().numpy(), eng.accept(got, 1.0))
+    # depth set / unset on device-resident records == the host-buffer calls
+    eng.depth_reset(); eng.depth_set_device(n, d_par.data_ptr()); torch.cuda.synchronize()
+    a = [eng.download_depth(c, l) for c in range(len(sc.cameras)) for l in range(6)]
+    eng.depth_reset(); eng.depth_set(parents)
+    b = [eng.download_depth(c, l) for c in range(len(sc.cameras)) for l in range(6)]
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and any((x < 1000).any() for x in a)
+    eng.depth_set_device(n // 2, d_par.data_ptr(), subtract=True); torch.cuda.synchronize()
+    c1 = [eng.download_depth(c, l) for c in range(len(sc.cameras)) for l in range(6)]
+    eng.depth_reset(); eng.depth_set(parents); eng.depth_unset(np.ascontiguousarray(parents[:n // 2]))
+    c2 = [eng.download_depth(c, l) for c in range(len(sc.cameras)) for l in range(6)]
+    assert all(np.array_equal(x, y) for x, y in zip(c1, c2))
+    # subtracting gives cells back: fewer occupied cells than after the set, and the oracle agrees on the final maps
+    assert sum((x < 1000).sum() for x in c1) < sum((x < 1000).sum() for x in a)
+    orc.depth_reset(); po = to_oracle(parents); po["status"] = 0
+    orc.depth_set(po); orc.depth_unset(po[:n // 2])
+    assert all(np.array_equal(orc.depth(c, l), c1[c * 6 + l]) for c in range(len(sc.cameras)) for l in range(6))
