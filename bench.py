@@ -50,9 +50,11 @@ def parse_args(argv=None):
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="city100", choices=["city100", "plane8", "plane8x100k", "city500_4k", "city24", "tiny"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="patches in the cpu_baseline sample (0 = auto)")
-    ap.add_argument("--inflight", type=int, default=4, help="steps in flight (each on its own stream): >1 lets the next step's CTAs start on SMs the previous step has drained")
+    ap.add_argument("--inflight", type=int, default=8, help="steps in flight (each on its own stream): >1 lets the next step's CTAs start on SMs the previous step has drained")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-ncc", action="store_true", help="skip the stand-alone scoring kernel leg (profiling runs)")
+    ap.add_argument("--sim-world", type=int, default=0, help="tuning aid on ONE GPU: run rank 0's shard of an N-way sub-tree split (not a bench line)")
+    ap.add_argument("--subtrees-per-rank", type=int, default=16, help="the sub-tree split continues until there are max(100, this x ranks) sub-trees")
     return ap.parse_args(argv)
 
 
@@ -255,14 +257,14 @@ def _claim_stdout():
     return real
 
 
-def shard_for_rank(workload, seeds_all, rank, world):
+def shard_for_rank(workload, seeds_all, rank, world, per_rank=16):
     """Strong-scaling split of a fixed seed batch: the reference's sub-tree split of the octree over the seed points
     (hpmvs_shard_cells = getSubTrees, src/main.cpp:50-96), sub-trees dealt to the ranks.  Returns (my seeds, info)."""
     from hpmvs_b200 import gather
     if world == 1 or workload not in STRONG:
         return seeds_all, None
     origin, width = gather.root_cube(seeds_all)
-    cell, rk, ncell = gather.shard_cells(seeds_all, origin, width, max(100, 16 * world), world)
+    cell, rk, ncell = gather.shard_cells(seeds_all, origin, width, max(100, per_rank * world), world)
     counts = np.bincount(rk[rk >= 0], minlength=world)
     info = {"subtrees": int(ncell), "seeds_per_rank": counts.tolist(), "origin": origin.tolist(), "root_width": width}
     return np.ascontiguousarray(seeds_all[rk == rank]), info
@@ -309,7 +311,7 @@ def main():
     t_upload = time.perf_counter() - t_setup0
     seeds_all, valid = hp.seed_patches(opts, eng.cameras, scene.points, scene.meas_offsets, scene.meas_cam)
     seeds_all = np.ascontiguousarray(seeds_all[valid])
-    seeds, shard_info = shard_for_rank(args.workload, seeds_all, rank, world)
+    seeds, shard_info = shard_for_rank(args.workload, seeds_all, rank, args.sim_world or world, args.subtrees_per_rank)
     n = len(seeds)
     n_step_cfg = len(seeds_all)
     hbm_used = torch.cuda.mem_get_info()
@@ -443,7 +445,7 @@ def main():
     clocks = sampler.finish() if sampler else None
     out_np = h_out.numpy().view(hp.PATCH_DTYPE).reshape(n)
     status_hist = np.bincount(out_np["status"], minlength=14).tolist()
-    for ho in h_outs[1:]:
+    for ho in h_outs[1:min(F, args.steps)]:
         assert np.array_equal(ho.numpy(), h_out.numpy()), "overlapping batches must return identical records"
     torch.cuda.set_stream(stream)
 
@@ -476,7 +478,11 @@ def main():
     # ---- reduce over ranks -------------------------------------------------------------------------------------
     stats = torch.tensor([t_dev, t_e2e, ok_per_step, tex_per_step, float(n), evals_per_step, float(ok_e2e), gather_s[0]],
                          dtype=torch.float64, device="cuda")
+    per_rank_ms = None
     if dist is not None:
+        allt = torch.zeros(world, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allt, stats[:1].clone())
+        per_rank_ms = [round(1e3 * float(v) / args.steps, 3) for v in allt.cpu().tolist()]
         mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         t_dev_max, t_e2e_max, gather_max = float(mx[0]), float(mx[1]), float(mx[7])
@@ -522,7 +528,7 @@ def main():
                         "parallelism": (f"octree sub-trees dealt to {world} ranks (getSubTrees split), scene replicated, no data-path collective; "
                                         "final gather to rank 0 + border de-dup inside e2e") if strong else
                                        f"patch shards x{world}, scene replicated, no data-path collective",
-                        "shards": shard_info, "wall_s_timed_region": t_wall, "e2e_gather_dedup_ms_per_step": 1e3 * gather_max / args.steps,
+                        "shards": shard_info, "device_ms_per_step_by_rank": per_rank_ms, "wall_s_timed_region": t_wall, "e2e_gather_dedup_ms_per_step": 1e3 * gather_max / args.steps,
                         "patches_gathered_kept": merged if dist is not None and strong else None,
                         "scene_upload_s": t_upload, "scene_upload_note": "render + upload + pyramid, streamed view by view" if args.workload == "city500_4k" else "upload + pyramid",
                         "hbm_used_gb": hbm_used_gb},

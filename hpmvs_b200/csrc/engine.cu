@@ -57,7 +57,7 @@ inline void h_normalized3(const float* a, float* o) {
 
 }  // namespace
 
-enum { HP_RING = 4, HP_WF_PARTS = 8, HP_WF_BATCHES = 8 };   // wavefront: up to 8 launches in flight, each with its own slots
+enum { HP_RING = 4, HP_WF_PARTS = 8, HP_WF_BATCHES = 16 };   // wavefront: up to 16 launches in flight, each with its own slots
 #ifndef HP_WF_DEFAULT_MODE
 #define HP_WF_DEFAULT_MODE (-1)     // auto: wavefront kernels for large batches, the persistent kernel below wf_min_batch patches
 #endif
@@ -91,7 +91,7 @@ struct hpmvs_engine {
     size_t cap_patches = 0, cap_inccs = 0;
     // hpmvs_optimize_batch_submit: a second staging set so that two host-buffer batches can be in flight
     struct Stage { hpmvs_patch_t* d_in = nullptr; hpmvs_patch_t* d_out = nullptr; size_t cap = 0; double* d_start = nullptr;
-                   double* h_start = nullptr; size_t cap_start = 0; cudaEvent_t done = nullptr; } stage2[8];
+                   double* h_start = nullptr; size_t cap_start = 0; cudaEvent_t done = nullptr; } stage2[16];
     unsigned long long submit_seq = 0;
     int start_mode = 0;              // hpmvs_engine_set_start_mode
     double* d_start = nullptr;       // host-evaluated start angles of the batch (start_mode 1)
@@ -119,7 +119,9 @@ struct hpmvs_engine {
     // wavefront form of the fused path (patch_kernels_wf.cuh): 0 = persistent kernels, 1 = per-phase kernels in a CUDA-graph WHILE loop,
     // 2 = the same kernels launched round by round from the host (debugging; the call blocks), -1 = 1 for batches >= wf_min_batch else 0
     int wf_mode = 0;
-    int wf_min_batch = 20000;        // measured cross-over (profiles/r2_wavefront_experiments.md): 10 k patches 19 ms persistent vs 24 ms wavefront
+    int wf_min_batch = 20000;        // synchronous call (one batch at a time): 10 k patches 24.5 ms persistent vs ~35 ms wavefront, 44 k: 88 vs 77 ms
+    int wf_min_batch_async = 4000;   // asynchronous / device-resident calls (the caller keeps several batches in flight): with 8 in flight the
+                                     // wavefront kernels win from ~5 k patches on (5.5 k: 10.1 vs 15.9 ms, 11 k: 16.0 vs 22.4 ms per step)
     int wf_split = 0;                // 1: advance phases A / T / B as three kernels, 0: one kernel with every phase (default: 61.5 vs 71.7 ms per city100 step)
     int wf_capacity = 0;             // slots in flight per wavefront context
     struct WfContext {
@@ -301,7 +303,7 @@ int hpmvs_engine_create(const hpmvs_options_t* opt, int device, hpmvs_engine_t**
     e->wf_mode = HP_WF_DEFAULT_MODE;
     if (const char* wf = getenv("HPMVS_WF")) e->wf_mode = atoi(wf);
     if (const char* ws = getenv("HPMVS_WF_SPLIT")) e->wf_split = atoi(ws);
-    if (const char* wm = getenv("HPMVS_WF_MIN_BATCH")) e->wf_min_batch = atoi(wm);
+    if (const char* wm = getenv("HPMVS_WF_MIN_BATCH")) e->wf_min_batch = e->wf_min_batch_async = atoi(wm);
     e->wf_capacity = e->sm_count * 12 * 32;                                 // one full wave of advance threads (12 warps per SM)
     if (const char* wp = getenv("HPMVS_WF_PARTS")) e->wf_parts = atoi(wp);
     if (e->wf_parts < 1) e->wf_parts = 1;
@@ -712,13 +714,13 @@ static int launch_wavefront(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, h
     return 0;
 }
 
-static int launch_optimize(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, hpmvs_patch_t* d_out, cudaStream_t s) {
+static int launch_optimize(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, hpmvs_patch_t* d_out, cudaStream_t s, bool async_call = true) {
     HP_NVTX("hpmvs:launch_optimize");
     int rc = check_ready(e);
     if (rc) return rc;
     rc = sync_cameras(e);
     if (rc) return rc;
-    if (e->wf_mode > 0 || (e->wf_mode < 0 && n >= e->wf_min_batch)) return launch_wavefront(e, n, d_in, d_out, s);
+    if (e->wf_mode > 0 || (e->wf_mode < 0 && n >= (async_call ? e->wf_min_batch_async : e->wf_min_batch))) return launch_wavefront(e, n, d_in, d_out, s);
     // launches on different streams overlap (a CTA of the next launch starts on an SM as soon as the previous launch's CTA
     // there has drained its slots): every launch gets its own work counter from a small ring; a ring slot is reused only after
     // the launch that used it last has completed
@@ -838,7 +840,7 @@ int hpmvs_optimize_batch(hpmvs_engine_t* e, int n, const hpmvs_patch_t* in, hpmv
         HP_CUDA(cudaMemcpyAsync(e->d_start, e->h_start, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, s));
         e->next_start = e->d_start;
     }
-    rc = launch_optimize(e, n, e->d_in, e->d_out, s);
+    rc = launch_optimize(e, n, e->d_in, e->d_out, s, /*async_call=*/false);
     if (rc) return rc;
     HP_CUDA(cudaMemcpyAsync(out, e->d_out, sizeof(hpmvs_patch_t) * n, cudaMemcpyDeviceToHost, s));
     HP_CUDA(cudaStreamSynchronize(s));
@@ -859,7 +861,7 @@ int hpmvs_optimize_batch_submit(hpmvs_engine_t* e, int n, const hpmvs_patch_t* i
     int rc = check_ready(e);
     if (rc) return rc;
     if (!valid_view_ids(e, n, in)) return HPMVS_E_ARG;
-    hpmvs_engine::Stage& st = e->stage2[e->submit_seq++ % 8];
+    hpmvs_engine::Stage& st = e->stage2[e->submit_seq++ % 16];
     if (!st.done) HP_CUDA(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
     if ((size_t)n > st.cap) {
         HP_CUDA(cudaEventSynchronize(st.done));
