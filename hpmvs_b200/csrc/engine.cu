@@ -77,6 +77,8 @@ struct hpmvs_engine {
     std::vector<std::vector<size_t>> depth_cells;   // [cam][level] floats allocated (a camera table with other image sizes reallocates)
     int* d_accept = nullptr;
     size_t cap_accept = 0;
+    int ncc_tma = 0;                    // HPMVS_NCC_TMA=1: the scoring kernel stages its image windows with the bulk-async copy engine (A/B experiment)
+    unsigned long long* d_tma_fallbacks = nullptr;
     unsigned char* d_dedup = nullptr;   // hash table + per-record slots of hpmvs_dedup_border_device
     size_t cap_dedup = 0;
     hp::DevCamera* d_cams = nullptr;
@@ -144,6 +146,7 @@ struct hpmvs_engine {
     } wfb[HP_WF_BATCHES];
     int wf_parts = 1;                // a batch is cut into up to this many sub-batches: their round loops interleave on the GPU
     unsigned long long wf_seq = 0;
+    int wf_last = 0;                 // batch context of the most recent wavefront launch
     unsigned long long wf_overruns = 0;
     std::mutex mu;
 };
@@ -291,6 +294,12 @@ int hpmvs_engine_create(const hpmvs_options_t* opt, int device, hpmvs_engine_t**
                                                           e->smem_bytes));
     if (e->blocks_per_sm < 1) e->blocks_per_sm = 1;
     if (const char* fl = getenv("HPMVS_FORCE_LANES")) e->force_lanes = atoi(fl);
+    if (const char* tm = getenv("HPMVS_NCC_TMA")) e->ncc_tma = atoi(tm);
+    if (e->ncc_tma) {
+        HP_CUDA(cudaFuncSetAttribute(hp::ncc_kernel_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(hp::NccWarpTma) * hp::WARPS_PER_BLOCK)));
+        HP_CUDA(cudaMalloc(&e->d_tma_fallbacks, sizeof(unsigned long long)));
+        HP_CUDA(cudaMemset(e->d_tma_fallbacks, 0, sizeof(unsigned long long)));
+    }
     if (const char* pk = getenv("HPMVS_PARKED")) e->parked_mode = atoi(pk);
     e->pvariant = g_default_pvariant;
     if (const char* cfg = getenv("HPMVS_PCONFIG")) {
@@ -329,7 +338,7 @@ void hpmvs_engine_destroy(hpmvs_engine_t* e) {
     for (auto& cam : e->depths)
         for (auto* d : cam)
             if (d) cudaFree(d);
-    cudaFree(e->d_accept); cudaFree(e->d_dedup);
+    cudaFree(e->d_accept); cudaFree(e->d_dedup); cudaFree(e->d_tma_fallbacks);
     for (int i = 0; i < 2; i++) if (e->pool_done[i]) cudaEventDestroy(e->pool_done[i]);
     cudaFree(e->d_cams); cudaFree(e->d_covis_off); cudaFree(e->d_covis_ids);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_inccs); cudaFree(e->d_stage);
@@ -672,10 +681,27 @@ static int wf_prepare_part(hpmvs_engine* e, hpmvs_engine::WfContext& w, int n, c
 // A batch is cut into up to wf_parts contiguous sub-batches, each with its own round loop (own slots, lists, WHILE node) in ONE graph.
 // Every round of a sub-batch is a chain of latency-bound kernels (ncu: the SMs are > 85 % idle during an advance kernel), so the
 // branches interleave on the GPU: while one sub-batch is in its optimizer phase others sample.
+// Choose an in-flight slot (wavefront batch context / host-buffer staging set): an idle one that already owns its buffers, else a fresh
+// one (buffers + graph are created on first use: tens of milliseconds), else the oldest (the caller's stream then waits for it).  The
+// number of slots that ever get created is thus the number of launches the caller really keeps in flight.
+}  // extern "C"
+template <class Slot>
+static int pick_slot(Slot* a, int n, unsigned long long& rr) {
+    int fresh = -1;
+    for (int i = 0; i < n; i++) {
+        if (!a[i].done) { if (fresh < 0) fresh = i; continue; }
+        if (cudaEventQuery(a[i].done) == cudaSuccess) return i;
+    }
+    if (fresh >= 0) return fresh;
+    return (int)(rr++ % (unsigned long long)n);
+}
+extern "C" {
+
 static int launch_wavefront(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, hpmvs_patch_t* d_out, cudaStream_t s) {
     const double* d_start = e->next_start;
     e->next_start = nullptr;
-    hpmvs_engine::WfBatch& b = e->wfb[e->wf_seq++ % HP_WF_BATCHES];
+    e->wf_last = pick_slot(e->wfb, (int)HP_WF_BATCHES, e->wf_seq);
+    hpmvs_engine::WfBatch& b = e->wfb[e->wf_last];
     int rc;
     for (int k = 0; k < e->wf_parts; k++) if ((rc = wf_ensure_context(e, b.part[k]))) return rc;
     if (!b.done) HP_CUDA(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
@@ -861,7 +887,7 @@ int hpmvs_optimize_batch_submit(hpmvs_engine_t* e, int n, const hpmvs_patch_t* i
     int rc = check_ready(e);
     if (rc) return rc;
     if (!valid_view_ids(e, n, in)) return HPMVS_E_ARG;
-    hpmvs_engine::Stage& st = e->stage2[e->submit_seq++ % 16];
+    hpmvs_engine::Stage& st = e->stage2[pick_slot(e->stage2, 16, e->submit_seq)];
     if (!st.done) HP_CUDA(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
     if ((size_t)n > st.cap) {
         HP_CUDA(cudaEventSynchronize(st.done));
@@ -944,7 +970,13 @@ int hpmvs_ncc_batch_device(hpmvs_engine_t* e, int n, const hpmvs_patch_t* d_in, 
     const int need = (n + hp::WARPS_PER_BLOCK - 1) / hp::WARPS_PER_BLOCK;
     if (need < grid) grid = need;
     HP_CUDA(cudaEventRecord(e->ev0, s));
-    hp::ncc_kernel<<<grid, hp::WARPS_PER_BLOCK * 32, e->smem_bytes, s>>>(K, ref_idx, robust, d_inccs);
+    if (e->ncc_tma) {
+        int g2 = e->sm_count * 3;                              // ~70 KB per CTA: 3 CTAs (12 warps) per SM
+        if (need < g2) g2 = need;
+        hp::ncc_kernel_tma<<<g2, hp::WARPS_PER_BLOCK * 32, sizeof(hp::NccWarpTma) * hp::WARPS_PER_BLOCK, s>>>(K, ref_idx, robust, d_inccs, e->d_tma_fallbacks);
+    } else {
+        hp::ncc_kernel<<<grid, hp::WARPS_PER_BLOCK * 32, e->smem_bytes, s>>>(K, ref_idx, robust, d_inccs);
+    }
     HP_CUDA(cudaEventRecord(e->ev1, s));
     e->launches++;
     HP_CUDA(cudaGetLastError());
@@ -1147,13 +1179,23 @@ int hpmvs_engine_download_depth(hpmvs_engine_t* e, int cam, int level, float* ou
     return 0;
 }
 
+// debugging aid (not in the header): textures of the TMA-staged scoring kernel whose footprint did not fit the staged window
+long long hpmvs_engine_tma_fallbacks(hpmvs_engine_t* e) {
+    if (!e || !e->d_tma_fallbacks) return -1;
+    unsigned long long v = 0;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    cudaMemcpy(&v, e->d_tma_fallbacks, sizeof(v), cudaMemcpyDeviceToHost);
+    return (long long)v;
+}
+
 // debugging aid (not in the header): writes the per-round log of the most recent wavefront launch as CSV (needs HPMVS_WF_LOG at create)
 int hpmvs_engine_dump_round_log(hpmvs_engine_t* e, const char* path) {
     if (!e || !path) return HPMVS_E_ARG;
     std::lock_guard<std::mutex> lk(e->mu);
     HP_CUDA(cudaSetDevice(e->device));
     HP_CUDA(cudaDeviceSynchronize());
-    hpmvs_engine::WfContext& w = e->wfb[(e->wf_seq + HP_WF_BATCHES - 1) % HP_WF_BATCHES].part[0];
+    hpmvs_engine::WfContext& w = e->wfb[e->wf_last].part[0];
     if (!w.round_log) return HPMVS_E_STATE;
     hp::WfCtl c;
     HP_CUDA(cudaMemcpy(&c, w.ctl, sizeof(c), cudaMemcpyDeviceToHost));

@@ -253,6 +253,7 @@ __device__ __forceinline__ bool view_setup(const KParams& K, const DevCamera& ca
     if (mnx < (float)m || mny < (float)m || mxx >= (float)(cam.w[lvl] - m) || mxy >= (float)(cam.h[lvl] - m)) return false;
     vs.tlx = tlx; vs.tly = tly; vs.dxx = dxx; vs.dxy = dxy; vs.dyx = dyx; vs.dyy = dyy;
     vs.pitch = cam.pitch[lvl];
+    vs.pad = cam.h[lvl];            // rows of the level (the staged-window variant of the scoring kernel checks its window against them)
     vs.img = cam.img[lvl];
     return true;
 }
@@ -1397,6 +1398,168 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) ncc_kernel(const KParams
             if (lane < P.nimg) v = W.incc[lane];
         }
         inccs[(size_t)pi * MAXV + lane] = (lane < P.nimg) ? v : 0.0f;
+        if (lane == 0) c_tex += P.textures;
+        __syncwarp();
+    }
+    if (lane == 0 && c_tex) atomicAdd(&K.counters[3], c_tex);
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// K1-staged: the same scoring (setINCCs for a batch) with the per-view image window of every texture STAGED IN SHARED MEMORY BY THE
+// BULK-ASYNC COPY ENGINE (north_star: "TMA staging per-view tiles into shared memory") - the A/B that closes the question
+// (profiles/r2_tma_ab.md).  For every texture of a group the TWR rows of a TWC-pixel window at the footprint's
+// corner (start column rounded down to 16 bytes) are fetched with cp.async.bulk (SASS UBLKCP, the engine the parked kernel already
+// uses) onto the warp's mbarrier - 4 row copies per lane; after the wait the 49 x 4 bilinear taps read the window with LDS instead
+// of LDG.  A footprint that does not fit the window falls back to the global loads for that view.  Same arithmetic, same results.
+// (A first version used one 2-D tensor map per view and level and cp.async.bulk.tensor.2d, SASS UTMALDG: it compiled, but every launch
+// died with "illegal instruction" at the UTMALDG - with the descriptors in global memory and the boxes issued from a loop - and
+// could not be debugged further inside this round's GPU budget; the row form moves the same bytes through the same engine.)
+// ----------------------------------------------------------------------------------------------------------
+constexpr int TWC = 20, TWR = 16;         // window: 20 pixels (80 bytes, 16-byte multiples) x 16 rows
+struct __align__(128) NccWarpTma {
+    uchar4 win[VC][TWR * TWC];            // 10 KB
+    Scratch S;
+    LaneCtx P;
+    unsigned long long mbar;
+    int wx0[VC], wy0[VC], wok[VC];
+};
+// Image::getColor on a staged window (same taps, same accumulation order as get_color)
+__device__ __forceinline__ f3 get_color_win(const uchar4* win, int wx0, int wy0, float x, float y) {
+    const int lx = (int)x, ly = (int)y;
+    const float dx1 = x - (float)lx, dx0 = 1.0f - dx1;
+    const float dy1 = y - (float)ly, dy0 = 1.0f - dy1;
+    const float f00 = dx0 * dy0, f01 = dx0 * dy1, f10 = dx1 * dy0, f11 = dx1 * dy1;
+    const uchar4* p = win + (ly - wy0) * TWC + (lx - wx0);
+    const uchar4 a = p[0], b = p[1], c = p[TWC], d = p[TWC + 1];
+    f3 o;
+    o.x = ((float)a.x * f00 + (float)c.x * f01) + ((float)b.x * f10 + (float)d.x * f11);
+    o.y = ((float)a.y * f00 + (float)c.y * f01) + ((float)b.y * f10 + (float)d.y * f11);
+    o.z = ((float)a.z * f00 + (float)c.z * f01) + ((float)b.z * f10 + (float)d.z * f11);
+    return o;
+}
+__device__ __forceinline__ void sample_one_win(NccWarpTma& Wt, int idx) {
+    Scratch& W = Wt.S;
+    const int slot = idx / 49, s = idx - 49 * slot;
+    const ViewSetup& v = W.vs[W.slot_view[slot]];
+    const int yy = s / 7, xx = s - 7 * yy;
+    const float dyx = v.dyx, dyy = v.dyy, dxx = v.dxx, dxy = v.dxy;
+    float px = v.tlx, py = v.tly;
+#pragma unroll
+    for (int i = 0; i < 6; i++) if (i < yy) { px += dyx; py += dyy; }
+#pragma unroll
+    for (int i = 0; i < 6; i++) if (i < xx) { px += dxx; py += dxy; }
+    const f3 col = Wt.wok[slot] ? get_color_win(Wt.win[slot], Wt.wx0[slot], Wt.wy0[slot], px, py) : get_color(v.img, v.pitch, px, py);
+    float* t = W.tex[slot] + 3 * s;
+    t[0] = col.x; t[1] = col.y; t[2] = col.z;
+}
+// stage the windows of slots [first, first+ns)
+__device__ __forceinline__ void stage_windows(NccWarpTma& Wt, const LaneCtx& P, const KParams& K, int first, int ns,
+                                              int lane, unsigned& phase, unsigned long long* fallbacks) {
+    Scratch& W = Wt.S;
+    bool fits = false;
+    if (lane < ns) {
+        const int slot = first + lane;
+        const ViewSetup& v = W.vs[W.slot_view[slot]];
+        // the footprint's bounding box from its four corners (the grid is affine in the sample index)
+        const float ex = 6.0f * v.dxx, ey = 6.0f * v.dxy, fx = 6.0f * v.dyx, fy = 6.0f * v.dyy;
+        const float mnx = v.tlx + fminf(0.0f, ex) + fminf(0.0f, fx) - 0.01f, mxx = v.tlx + fmaxf(0.0f, ex) + fmaxf(0.0f, fx) + 0.01f;
+        const float mny = v.tly + fminf(0.0f, ey) + fminf(0.0f, fy) - 0.01f, mxy = v.tly + fmaxf(0.0f, ey) + fmaxf(0.0f, fy) + 0.01f;
+        const int x0 = ((int)mnx) & ~3, y0 = (int)mny;               // 16-byte aligned start column (rows are 16-byte aligned: pitch % 4 == 0)
+        fits = ((int)mxx + 1 < x0 + TWC) && ((int)mxy + 1 < y0 + TWR) && mnx >= 0.0f && mny >= 0.0f &&
+               x0 + TWC <= v.pitch && y0 + TWR <= v.pad + 2;      // the window stays inside the level's allocation (pitch x (rows + 2))
+        Wt.wx0[slot] = x0; Wt.wy0[slot] = y0; Wt.wok[slot] = fits ? 1 : 0;
+        if (!fits && fallbacks) atomicAdd(fallbacks, 1ull);
+    }
+    const unsigned m = __ballot_sync(FULL, fits);
+    __syncwarp();
+    if (m) {
+        fence_proxy_async();       // the windows were last read through the generic proxy
+        if (lane == 0) mbar_expect_tx(&Wt.mbar, (unsigned)__popc(m) * TWR * TWC * 4u);
+        __syncwarp();
+        // lane = (slot, quarter of the rows): up to 8 slots x 4 quarters, 4 row copies each
+        const int sj = lane >> 2, q = lane & 3;
+        if (sj < ns && ((m >> sj) & 1u)) {
+            const int slot = first + sj;
+            const ViewSetup& v = W.vs[W.slot_view[slot]];
+            const int x0 = Wt.wx0[slot], y0 = Wt.wy0[slot];
+#pragma unroll
+            for (int r = 4 * q; r < 4 * q + 4; r++)
+                bulk_g2s(&Wt.win[slot][r * TWC], v.img + (size_t)(y0 + r) * v.pitch + x0, TWC * 4u, &Wt.mbar);
+        }
+        // bounded wait: a faulting copy must end in a trap, never in a hang
+        unsigned okw = 0;
+        for (unsigned tries = 0; !okw; tries++) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(okw) : "r"(smem_u32(&Wt.mbar)), "r"(phase) : "memory");
+            if (tries > (1u << 24)) __trap();
+        }
+        phase ^= 1u;
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) ncc_kernel_tma(const KParams K, int ref_idx, int robust,
+                                                                       float* inccs, unsigned long long* fallbacks) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    NccWarpTma& Wt = reinterpret_cast<NccWarpTma*>(smem_raw)[threadIdx.x >> 5];
+    Scratch& W = Wt.S;
+    LaneCtx& P = Wt.P;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    if (lane == 0) { mbar_init(&Wt.mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncwarp();
+    unsigned phase = 0;
+    unsigned long long c_tex = 0;
+    for (int pi = warp; pi < K.n; pi += nwarps) {
+        load_patch(P, K.in[pi], pi, lane);
+        const int nimg = P.nimg;
+        float v = 2.0f;
+        if (ref_idx < nimg) {
+            // set_inccs / eval_dots (above) with the sampling stage reading staged windows
+            const f4 c = ld4(P.center), n = ld4(P.normal);
+            f4 xa, ya, za;
+            patch_axes(K.cams[P.images[ref_idx]], n, P.scale, xa, ya, za);
+            bool ok = false;
+            if (lane < nimg) {
+                ViewSetup vs;
+                ok = view_setup(K, K.cams[P.images[lane]], c, P.scale, xa, ya, n, vs);
+                if (ok) W.vs[lane] = vs;
+                W.vvalid[lane] = ok ? 1 : 0;
+            }
+            const unsigned vmask = __ballot_sync(FULL, ok);
+            __syncwarp();
+            if ((vmask >> ref_idx) & 1u) {
+                const unsigned omask = vmask & ~(1u << ref_idx);
+                if (ok && lane != ref_idx) W.vlist[__popc(omask & ((1u << lane) - 1u))] = lane;
+                const int nother = __popc(omask);
+                if (lane == 0) { P.textures += 1 + nother; W.slot_view[0] = ref_idx; }
+                __syncwarp();
+                int done = 0;
+                bool first = true;
+                do {
+                    const int no = min(VC - 1, nother - done);
+                    if (lane < no) W.slot_view[1 + lane] = W.vlist[done + lane];
+                    __syncwarp();
+                    const int s0 = first ? 0 : 1, ns = first ? 1 + no : no;
+                    stage_windows(Wt, P, K, s0, ns, lane, phase, fallbacks);
+                    for (int base = s0 * 49 + lane; base < (s0 + ns) * 49; base += 32) sample_one_win(Wt, base);
+                    __syncwarp();
+                    stats_slots(W, s0, ns, lane);
+                    if (first) normalize_ref(W, lane);
+                    if (no > 0) dot_slots(W, no, lane);
+                    done += no;
+                    first = false;
+                } while (done < nother);
+            }
+            if (lane < nimg) {
+                if (!W.vvalid[ref_idx]) v = 2.0f;
+                else if (lane == ref_idx) v = 0.0f;
+                else if (!W.vvalid[lane]) v = 2.0f;
+                else { const float r = 1.0f - W.dots[lane]; v = robust ? r / (1.0f + 3.0f * r) : r; }
+            }
+        }
+        inccs[(size_t)pi * MAXV + lane] = (lane < nimg) ? v : 0.0f;
         if (lane == 0) c_tex += P.textures;
         __syncwarp();
     }

@@ -1,0 +1,13 @@
+#!/bin/bash
+O=gpurun_out/r2t; mkdir -p $O
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "tma or wavefront or overlapping" > $O/pytest_tma.txt 2>&1; tail -3 $O/pytest_tma.txt
+r() { name=$1; shift; timeout 400 python bench.py --no-cpu --no-ncc "$@" > $O/$name.json 2>$O/$name.err; python -c "
+import json
+d=json.loads(open('$O/$name.json').read().strip().splitlines()[-1]); print('$name: n %d value %.0f e2e %.0f ms %.2f'%(d['run']['patches_per_step_this_rank'], d['value'],d['e2e']['value'],d['ms_per_step']))"; }
+for f in 4 8 12; do r city100_if$f --inflight $f --steps 20 --warmup 5; done
+for f in 4 8 12; do r sw4_if$f --sim-world 4 --inflight $f --steps 20 --warmup 5; done
+for f in 4 8 12 16; do r sw8_if$f --sim-world 8 --inflight $f --steps 20 --warmup 5; done
+for f in 4 8 16; do r plane8_if$f --workload plane8 --inflight $f --steps 20 --warmup 5; done
+for t in 0 1; do HPMVS_NCC_TMA=$t timeout 300 python bench.py --no-cpu --steps 4 > $O/ncc_tma$t.json 2> $O/ncc_tma$t.err; python -c "
+import json
+d=json.loads(open('$O/ncc_tma$t.json').read().strip().splitlines()[-1]); r=d['roofline_ncc']; print('ncc tma=$t: frac %.4f launch ms %.3f scores/s %.0f'%(r['frac'], r['launch_ms'], r['patch_scores_per_s']))"; done

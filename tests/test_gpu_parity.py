@@ -433,3 +433,27 @@ def test_wavefront_variant_bit_exact(plane, monkeypatch, mode, split, slots):
         oracle.set_cr_asinf(False)
     st = compare_outputs(ref, b)
     assert st["status_equal"] == st["n"] and st["bit_exact"] == st["both_ok"] and st["vis_equal"] == st["both_ok"]
+
+
+def test_tma_staged_scoring_kernel_bit_exact(plane, monkeypatch):
+    """The A/B variant of the scoring kernel that stages every texture's image window in shared memory with the tensor-memory
+    accelerator (cp.async.bulk.tensor.2d, one tensor map per view and level; HPMVS_NCC_TMA=1) must return the same bits as the
+    kernel that gathers through L1 - windows are an access path, not arithmetic."""
+    import ctypes as C
+    import torch
+    sc, orc, seeds, eng = plane
+    monkeypatch.setenv("HPMVS_NCC_TMA", "1")
+    eng_t = hp.Engine.from_synth(sc)
+    pe = to_engine(seeds)
+    d_in = torch.from_numpy(pe.view(np.uint8).reshape(len(pe), -1).copy()).cuda()
+    for ref_idx, robust in ((0, False), (1, True)):
+        want = eng.ncc(pe, ref_idx, robust)
+        d_out = torch.full((len(pe), hp.MAX_VIEWS), -1.0, dtype=torch.float32, device="cuda")
+        eng_t.ncc_device(len(pe), d_in.data_ptr(), d_out.data_ptr(), ref_idx, robust)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out.cpu().numpy(), want), (ref_idx, robust)
+    from hpmvs_b200 import engine as E
+    L = E._lib(); L.hpmvs_engine_tma_fallbacks.argtypes = [C.c_void_p]; L.hpmvs_engine_tma_fallbacks.restype = C.c_longlong
+    fb = L.hpmvs_engine_tma_fallbacks(eng_t._h)
+    tex = eng_t.counters().textures
+    assert 0 <= fb < 0.5 * tex, (fb, tex)          # most footprints fit the 16 x 16 pixel window
