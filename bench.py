@@ -539,9 +539,10 @@ def main():
                         "ms_per_step": 1e3 * t_e2e_max / args.steps, "start_mode": 1},
                 "gpu_launches": launches_timed,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic_of(args.workload), "peak_source": peak_src, "kernel": "hp::optimize_kernel",
+                             "traffic": traffic_of(args.workload), "peak_source": peak_src,
+                             "kernel": "one step of the fused path = hp::wf_post_kernel<fill> + rounds x (hp::wf_advance_kernel, hp::wf_eval_kernel, hp::wf_post_kernel) in a CUDA-graph WHILE loop (batches >= 4000 patches), else hp::optimize_kernel",
                              "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": 1e3 * mean_launch_s,
-                             "note": "algorithmic gather bytes (588 B/texture, no reuse credit); launch_ms = timed region / launches (launches of consecutive steps overlap when steps_in_flight > 1); the footprint is L1-resident so DRAM traffic is far lower - kernel is issue/latency bound, see DESIGN.md"},
+                             "note": "algorithmic gather bytes (588 B/texture, no reuse credit) of one step / device time of a step (timed region / steps; steps overlap when steps_in_flight > 1); traffic = DRAM bytes summed over all kernels of one step (profiles/traffic.json); the footprints are L1/L2 resident, the scoring kernel is instruction-issue bound and the optimizer kernel latency bound, see DESIGN.md section 5"},
                 "cpu_baseline": cpu}
         if ncc:
             nb = ncc["nb"]

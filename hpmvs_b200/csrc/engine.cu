@@ -670,6 +670,7 @@ static int wf_prepare_part(hpmvs_engine* e, hpmvs_engine::WfContext& w, int n, c
     P.ctl = w.ctl;
     P.cond = w.cond;
     P.use_cond = (e->wf_mode != 2) ? 1 : 0;
+    P.kernels_per_round = e->wf_split ? 5 : 3;
     P.round_log = w.round_log; P.round_log_cap = 65536;
     HP_CUDA(cudaMemcpyAsync(w.d_params, &P, sizeof(P), cudaMemcpyHostToDevice, s));
     HP_CUDA(cudaMemsetAsync(w.ctl, 0, sizeof(hp::WfCtl), s));
@@ -718,7 +719,7 @@ static int launch_wavefront(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, h
     }
     if (graph_mode) {
         HP_CUDA(cudaGraphLaunch(b.exec, s));
-        e->launches += (unsigned long long)used * (e->wf_split ? 6 : 4);    // kernels of a graph branch (fill + one round); rounds are counted on the device
+        e->launches += (unsigned long long)parts;                    // the fill kernels; the kernels of the rounds are counted on the device (wf_sched)
     } else {
         hpmvs_engine::WfContext& w = b.part[0];
         const WfLaunchShape sh = wf_shape(e, w);
@@ -727,7 +728,6 @@ static int launch_wavefront(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, h
         const int max_rounds = w.h_params[(w.seq + 1) % 2]->max_rounds;
         for (int live = 1, guard = 0; live && guard < max_rounds; guard += 4) {
             for (int r = 0; r < 4; r++) wf_enqueue_round(e, w, s);
-            e->launches += 4 * (e->wf_split ? 5 : 3);
             HP_CUDA(cudaMemcpyAsync(w.h_ctl, w.ctl, sizeof(hp::WfCtl), cudaMemcpyDeviceToHost, s));
             HP_CUDA(cudaStreamSynchronize(s));
             live = w.h_ctl->live;
@@ -1240,7 +1240,7 @@ int hpmvs_engine_counters(hpmvs_engine_t* e, hpmvs_counters_t* out, int reset) {
 #endif
     }
     out->patches = c[0]; out->patches_ok = c[1]; out->evals = c[2]; out->textures = c[3];
-    out->kernel_launches = e->launches;
+    out->kernel_launches = e->launches + c[13];                  // host-side launches + the round kernels of the wavefront graphs
     if (reset) {
         HP_CUDA(cudaMemset(e->d_counters, 0, sizeof(c)));
         e->launches = 0;

@@ -34,6 +34,12 @@ constexpr int VC = 8;            // texture slots resident per warp (slot 0 = re
 constexpr int TEXN = 147;        // 7*7*3 floats per texture (Patch2d.hpp:31,88)
 constexpr int TEXS = 148;        // padded stride: (148*slot) mod 32 distinct for 8 slots -> conflict-free chains
 constexpr int QS = 52;
+// The variance chain of PatchTex::normalize adds one term (f0^2 + f1^2) + f2^2 per sample; forming the terms inside the serial chain
+// costs 12 instructions per sample with one lane per texture.  HP_VAR_PREPASS forms them in a flattened pass (lane = sample) and leaves
+// a 2-instruction chain (load + add) - same terms, same order of additions, so the same bits.
+#ifndef HP_VAR_PREPASS
+#define HP_VAR_PREPASS 1
+#endif
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -103,6 +109,9 @@ struct __align__(16) Scratch {
         float tex[VC][TEXS];            // raw -> normalised -> product textures of the views being evaluated
         float rays[MAXV][4];            // view rays of the view-list stages (never live at the same time as tex)
     };
+#if HP_VAR_PREPASS
+    float sq[VC][QS];               // per-sample squared deviations (f0^2 + f1^2) + f2^2 of the textures being evaluated
+#endif
     float mean[VC][4];
     float sigma[VC];
     int slot_view[VC];
@@ -296,6 +305,25 @@ __device__ __forceinline__ void stats_slots(Scratch& W, int first, int ns, int l
         W.mean[slot][ch] = a / 49.0f;
     }
     __syncwarp();
+#if HP_VAR_PREPASS
+    for (int idx = lane; idx < 49 * ns; idx += 32) {
+        const int so = idx / 49, i = idx - 49 * so, slot = first + so;
+        const float* t = W.tex[slot] + 3 * i;
+        const float f0 = W.mean[slot][0] - t[0], f1 = W.mean[slot][1] - t[1], f2 = W.mean[slot][2] - t[2];
+        W.sq[slot][i] = f0 * f0 + f1 * f1 + f2 * f2;
+    }
+    __syncwarp();
+    if (lane < ns) {
+        const int slot = first + lane;
+        const float* q = W.sq[slot];
+        float a = 0.0f;
+#pragma unroll 7
+        for (int i = 0; i < 49; i++) a += q[i];
+        float sg = sqrtf(a / 147.0f);
+        if (sg == 0.0f) sg = 1.0f;
+        W.sigma[slot] = sg;
+    }
+#else
     if (lane < ns) {
         const int slot = first + lane;
         const float* t = W.tex[slot];
@@ -310,19 +338,30 @@ __device__ __forceinline__ void stats_slots(Scratch& W, int first, int ns, int l
         if (sg == 0.0f) sg = 1.0f;
         W.sigma[slot] = sg;
     }
+#endif
     __syncwarp();
 }
 
 // normalise the reference texture in place (Patch2d.hpp:73-83)
+// Element i = lane + 32k of a 147-float texture belongs to channel (lane + 32k) % 3 = (lane % 3 + 2k) % 3: the channel walks a fixed
+// rotation as k advances, so the per-element "% 3" (and, in dot_slots, the "/ 147" of a flattened index) is not needed.
+__device__ __forceinline__ float chan_mean(int c0, int k, float m0, float m1, float m2) {
+    const int r = (2 * k) % 3;                                   // compile-time after unrolling
+    // channel = (c0 + r) % 3
+    if (r == 0) return c0 == 0 ? m0 : (c0 == 1 ? m1 : m2);
+    if (r == 1) return c0 == 0 ? m1 : (c0 == 1 ? m2 : m0);
+    return c0 == 0 ? m2 : (c0 == 1 ? m0 : m1);
+}
 __device__ __forceinline__ void normalize_ref(Scratch& W, int lane) {
     const float sg = W.sigma[0];
-    const float m[3] = {W.mean[0][0], W.mean[0][1], W.mean[0][2]};
+    const float m0 = W.mean[0][0], m1 = W.mean[0][1], m2 = W.mean[0][2];
+    const int c0 = lane % 3;
 #pragma unroll
     for (int k = 0; k < 5; k++) {
         const int i = lane + 32 * k;
         if (i < TEXN) {
             float v = W.tex[0][i];
-            v -= m[i % 3];
+            v -= chan_mean(c0, k, m0, m1, m2);
             v /= sg;
             W.tex[0][i] = v;
         }
@@ -333,14 +372,25 @@ __device__ __forceinline__ void normalize_ref(Scratch& W, int lane) {
 // normalise slots [1, 1+no) and multiply with the normalised reference in one pass, then PatchTex::dot's
 // 147-term sequential chain (Patch2d.hpp:37-44), lane = slot
 __device__ __forceinline__ void dot_slots(Scratch& W, int no, int lane) {
-    const int total = no * TEXN;
-#pragma unroll 4
-    for (int idx = lane; idx < total; idx += 32) {
-        const int so = idx / TEXN, i = idx - TEXN * so, slot = 1 + so;
-        float v = W.tex[slot][i];
-        v -= W.mean[slot][i % 3];
-        v /= W.sigma[slot];
-        W.tex[slot][i] = W.tex[0][i] * v;
+    const int c0 = lane % 3;
+    float r[5];                                                   // this lane's elements of the normalised reference
+#pragma unroll
+    for (int k = 0; k < 5; k++) r[k] = (lane + 32 * k < TEXN) ? W.tex[0][lane + 32 * k] : 0.0f;
+    for (int so = 0; so < no; so++) {
+        const int slot = 1 + so;
+        const float sg = W.sigma[slot];
+        const float m0 = W.mean[slot][0], m1 = W.mean[slot][1], m2 = W.mean[slot][2];
+        float* t = W.tex[slot];
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const int i = lane + 32 * k;
+            if (i < TEXN) {
+                float v = t[i];
+                v -= chan_mean(c0, k, m0, m1, m2);
+                v /= sg;
+                t[i] = r[k] * v;
+            }
+        }
     }
     __syncwarp();
     if (lane < no) {

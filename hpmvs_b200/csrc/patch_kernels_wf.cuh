@@ -58,6 +58,7 @@ struct WfParams {
     WfCtl* ctl;
     cudaGraphConditionalHandle cond;   // WHILE node of the launch graph (graph mode)
     int use_cond;
+    int kernels_per_round;             // 3 (advance, eval, post) or 5 (advance phases A / T / B)
     unsigned long long* round_log;     // optional (HPMVS_WF_LOG): per round {globaltimer ns, eval_cnt, post_cnt, dead}
     int round_log_cap;
 };
@@ -99,6 +100,7 @@ __device__ __forceinline__ void wf_sched(const WfParams& P) {
     }
     c.eval_cnt = 0;
     if (c.run_post) { c.post_cnt = 0; c.post_ticket = 0; }     // the post pass of this round consumed the list
+    atomicAdd(&P.K.counters[13], (unsigned long long)P.kernels_per_round);   // launches are counted where they happen: on the device
     c.round = c.round + 1;
     // Post passes are batched: a pass costs the latency of one post-stage (several scoring evaluations per patch, ~100-200 us) whether
     // it serves one patch or ten thousand, so finished patches are collected and served when nothing else is left to do, or - while
