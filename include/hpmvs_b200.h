@@ -265,7 +265,8 @@ int  hpmvs_dedup_border_device(hpmvs_engine_t *e, int n, const hpmvs_patch_t *d_
 int  hpmvs_root_cube(int n, const hpmvs_patch_t *patches, double origin[3], double *width);
 /* Replaces getSubTrees (src/main.cpp:50-96; DynOctTree::getSubTrees, include/hpmvs/doctree.h:513-523) as a partition of a patch set:
  * split the root cube into its non-empty children, keep splitting the sub-tree with the most patches until there are >= min_subtrees
- * (or the biggest holds < 100, main.cpp:74); deal the sub-trees to nranks ranks, biggest first to the least loaded rank.
+ * (or the biggest holds < 100, main.cpp:74); deal the sub-trees to nranks ranks, costliest first (cost = sum of its patches' view
+ * counts) to the least loaded rank.
  * cell_of[i] / rank_of[i] = sub-tree / rank of patch i (-1 outside the cube).  Returns the number of sub-trees. */
 int  hpmvs_shard_cells(int n, const hpmvs_patch_t *patches, const double origin[3], double root_width, int min_subtrees, int nranks,
                        int32_t *cell_of, int32_t *rank_of);

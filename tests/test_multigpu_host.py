@@ -104,8 +104,9 @@ def test_shard_cells_is_the_reference_subtree_split():
         for i, (_, idx) in enumerate(subs):
             assert (cell[idx] == i).all()
             assert len(set(rk[idx].tolist())) == 1           # a sub-tree is never split over ranks
-        load = np.bincount(rk, minlength=world)
-        assert load.max() - load.min() <= max(len(s[1]) for s in subs)     # greedy biggest-first bound
+        # sub-trees are dealt costliest-first by the sum of their patches' view counts: the greedy bound holds for that weight
+        load = np.bincount(rk, weights=p["nimages"].astype(np.float64), minlength=world)
+        assert load.max() - load.min() <= max(p["nimages"][s[1]].sum() for s in subs)
     # a patch outside the cube belongs to nobody
     far = p[:3].copy(); far["center"][0, 0] = 1e3
     cell, rk, _ = gather.shard_cells(far, origin, width, 8, 2)
