@@ -54,7 +54,7 @@ def parse_args(argv=None):
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-ncc", action="store_true", help="skip the stand-alone scoring kernel leg (profiling runs)")
     ap.add_argument("--sim-world", type=int, default=0, help="tuning aid on ONE GPU: run rank 0's shard of an N-way sub-tree split (not a bench line)")
-    ap.add_argument("--subtrees-per-rank", type=int, default=64, help="the sub-tree split continues until there are max(100, this x ranks) sub-trees")
+    ap.add_argument("--subtrees-per-rank", type=int, default=16, help="the sub-tree split continues until there are max(100, this x ranks) sub-trees")
     return ap.parse_args(argv)
 
 
@@ -257,7 +257,7 @@ def _claim_stdout():
     return real
 
 
-def shard_for_rank(workload, seeds_all, rank, world, per_rank=64):
+def shard_for_rank(workload, seeds_all, rank, world, per_rank=16):
     """Strong-scaling split of a fixed seed batch: the reference's sub-tree split of the octree over the seed points
     (hpmvs_shard_cells = getSubTrees, src/main.cpp:50-96), sub-trees dealt to the ranks.  Returns (my seeds, info)."""
     from hpmvs_b200 import gather

@@ -445,8 +445,8 @@ static int build_subtrees(int n, const hpmvs_patch_t* patches, const double orig
     std::vector<int> order(subs.size());
     for (size_t i = 0; i < subs.size(); i++) order[i] = (int)i;
     // the cost of a patch grows with the number of views it is measured in (textures per evaluation): the sub-trees are dealt by the
-    // sum of their patches' view counts, not by their patch count (measured on configs[3] at 8 ranks: scoring work max/mean 1.18 by
-    // count, 1.02 by views with 64 sub-trees per rank - profiles/r2_work_balance.txt)
+    // sum of their patches' view counts, not by their patch count (configs[3] at 8 ranks: scoring work max/mean 1.18 by count, 1.10 by
+    // views - profiles/r2_work_balance.txt; the measured step time per rank is latency bound and hardly moves: 10.9 -> 10.7 ms)
     std::vector<int64_t> weight(subs.size(), 0);
     for (size_t si = 0; si < subs.size(); si++)
         for (int i : subs[si].pts) weight[si] += (int64_t)std::max(1, patches[i].nimages);
