@@ -521,11 +521,12 @@ def main():
             cpu = {"value": rate, "unit": "patches/s", "cores": threads, "kind": kind,
                    "sample": f"first {ns} of {len(seeds_all)} seed patches of the same batch, {okc} optimized, {dt:.2f} s wall; {how}"}
         line = {"metric": "optimized patches/sec", "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
-                "warmup": n_warm, "ms_per_step": 1e3 * t_dev_max / args.steps, "higher_is_better": True,
+                "warmup": args.warmup, "ms_per_step": 1e3 * t_dev_max / args.steps, "higher_is_better": True,
                 "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32 samples / f64 optimizer", "data": "synthetic",
                 "config": bench_config(args.workload, desc, n_step_cfg, len(scene.cameras), world),
                 "run": {"patches_per_step_this_rank": int(n), "patches_per_step_all_ranks": n_all, "optimized_per_step": ok_all,
                         "evals_per_step": evals_all, "textures_per_step": tex_all, "steps_in_flight": F,
+                        "warmup_launches": n_warm,      # max(W, 3, steps in flight): every in-flight slot is created before the timed region
                         "status_histogram_rank0": status_hist, "too_many_views_rank0": status_hist[13],
                         "parallelism": (f"octree sub-trees dealt to {world} ranks (getSubTrees split), scene replicated, no data-path collective; "
                                         "final gather to rank 0 + border de-dup inside e2e") if strong else

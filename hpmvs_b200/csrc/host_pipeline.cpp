@@ -406,8 +406,11 @@ static int build_subtrees(int n, const hpmvs_patch_t* patches, const double orig
     for (int i = 0; i < n; i++) {
         bool inside = true;
         for (int a = 0; a < 3; a++) {
-            const double rel = ((double)patches[i].center[a] - origin[a]) / root_width;
-            // the box is closed at the top in the reference (a centre on the max face sits in the last cell)
+            double rel = ((double)patches[i].center[a] - origin[a]) / root_width;
+            // the box is closed at the top in the reference (a centre on the max face sits in the last cell); the cube is the f32
+            // bounding box of these very centres (hpmvs_root_cube), so a centre ON a face may miss it by a rounding of origin / width
+            if (rel < 0.0 && rel > -1e-6) rel = 0.0;
+            if (rel > 1.0 && rel < 1.0 + 1e-6) rel = 1.0;
             if (!(rel >= 0.0 && rel <= 1.0)) { inside = false; break; }
             const double c = std::floor(rel * (double)(1u << MAXL));
             q[3 * (size_t)i + a] = (uint32_t)std::min(c, (double)((1u << MAXL) - 1));

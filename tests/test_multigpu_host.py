@@ -187,3 +187,25 @@ def test_device_dedup_equals_host_dedup():
         got = np.nonzero(keep.cpu().numpy())[0]
         assert got.tolist() == want.tolist(), trial
         assert int(nk.item()) == len(want)
+
+
+def test_subtree_table_agrees_with_the_per_patch_assignment():
+    """hpmvs_shard_subtrees (the split as a table of (level, cell key, rank), what hpmvs_pipeline_run looks centres up in) and
+    hpmvs_shard_cells (the split as a per-patch assignment) are two views of one partition."""
+    from hpmvs_b200 import pipeline
+    rng = np.random.default_rng(4)
+    p = _make(4000, 0, rng)
+    p["center"][:1500, :3] *= 0.15
+    origin, width = gather.root_cube(p)
+    for want_trees, world in ((8, 2), (64, 4), (200, 8)):
+        cell, rk, ncell = gather.shard_cells(p, origin, width, want_trees, world)
+        lvl, key, srk = pipeline.shard_subtrees(p, origin, width, want_trees, world)
+        assert len(lvl) == ncell and srk.max() < world
+        assert (cell >= 0).all()                               # the cube is the bounding box of these centres: nobody is outside
+        rel = np.clip((p["center"][:, :3].astype(np.float64) - origin) / width, 0.0, 1.0)
+        q = np.minimum(np.floor(rel * (1 << 20)), (1 << 20) - 1).astype(np.int64)
+        for s in range(ncell):
+            k = q >> (20 - int(lvl[s]))
+            inside = (k == key[s][None, :]).all(1)
+            assert np.array_equal(np.nonzero(inside)[0], np.nonzero(cell == s)[0]), s
+            assert (rk[inside] == srk[s]).all()
