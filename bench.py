@@ -48,7 +48,7 @@ def parse_args(argv=None):
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="city100", choices=["city100", "plane8", "plane8x100k", "city500_4k", "city24", "tiny"])
+    ap.add_argument("--workload", default="city100", choices=["city100", "plane8", "plane8x100k", "city500_4k", "city24", "tiny", "fountain11"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="patches in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--inflight", type=int, default=12, help="steps in flight (each on its own stream): >1 lets the next step's CTAs start on SMs the previous step has drained")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
@@ -245,6 +245,117 @@ def run_reference(args):
     _OUT.write(json.dumps(line) + "\n"); _OUT.flush()
 
 
+# ---- configs[2]: fountain-P11-style 11-view scene, the FULL expand -> optimize -> filter loop, 1 B200 vs the reference's own CLI --------
+def fountain_scene():
+    from hpmvs_b200 import synth
+    try:
+        import torch
+        synth.USE_GPU_RENDERER = torch.cuda.is_available()
+    except ImportError:
+        pass
+    n_pts = int(os.environ.get("HPMVS_FOUNTAIN_POINTS", "300"))
+    sc = synth.plane_scene(n_views=11, width=3072, height=2048, focal=2800.0, radius=10.0, arc_deg=100.0, n_seeds=n_pts,
+                           extent=3.0, seed=3, tex_size=2048, depth_noise=0.3, plane_half=9.0)
+    return sc, f"fountain-P11-style 11-view 3072x2048 synthetic NVM, {n_pts} NVM points, full expand->optimize->filter loop (BASELINE.json configs[2])"
+
+
+def fountain_quality(xyz, nz):
+    return {"patches": int(len(xyz)), "rms_distance_to_true_plane": float(np.sqrt(np.mean(xyz[:, 2] ** 2))) if len(xyz) else None,
+            "mean_abs_normal_z": float(np.mean(np.abs(nz))) if len(xyz) else None}
+
+
+def run_fountain(args):
+    """One step = one whole run of the loop on the scene.  GPU arm: hpmvs_pipeline_run (C++ level-synchronous driver behind the C ABI:
+    every batch crosses the ABI with host buffers, so value == e2e); reference arm: the reference's own command line
+    (oracle/_ref/hpmvs_ref = /root/reference/src compiled where it lies) on all host cores.  The schedulers differ (batches per level vs
+    priority queues per sub-tree), so the clouds are compared by count and accuracy, and the rate is patches of the FINAL cloud per second."""
+    import glob
+    import tempfile
+    sc, desc = fountain_scene()
+    config = {"workload": desc, "views": 11, "patches_per_step": "the final cloud of one run of the loop",
+              "rate": "patches in the final cloud / wall time of the loop (scene upload and seeding outside, as the reference logs it: main.cpp:142-185)"}
+    steps = max(1, min(args.steps, 3))
+    if args.impl == "reference":
+        from oracle import ref
+        tmp = tempfile.mkdtemp(prefix="hpmvs_f11_")
+        nvm = os.path.join(tmp, "scene.nvm")
+        import hpmvs_b200 as hp
+        hp.synth.write_nvm(sc, nvm)
+        threads = host_threads()
+        secs, fin = [], None
+        for k in range(steps):
+            t = time.perf_counter()
+            r = ref.run_cli(nvm, os.path.join(tmp, f"ref{k}"), threads=threads)
+            secs.append(time.perf_counter() - t)
+            assert r.returncode == 0, r.stderr[-2000:]
+            # the CLI reports its own loop time ("Done within X seconds", main.cpp:183-185); fall back to the wall time of the process
+            L = open(os.path.join(tmp, f"ref{k}", "patches-final.ply")).read().split("\n")
+            n = int([l for l in L[:20] if l.startswith("element vertex")][0].split()[2])
+            h = L.index("end_header") + 1
+            fin = np.array([[float(x) for x in l.split()[:10]] for l in L[h:h + n]], np.float64).reshape(n, 10)
+            import re
+            m = re.search(r"Done within ([0-9.eE+-]+) seconds", r.stderr + r.stdout)
+            if m:
+                secs[-1] = float(m.group(1))
+        levels = sorted(int(os.path.basename(f)[8:-4]) // 10 for f in glob.glob(os.path.join(tmp, f"ref{steps - 1}", "patches-[0-9]*.ply")))
+        val = len(fin) / (sum(secs) / len(secs))
+        line = {"impl": "reference", "metric": "optimized patches/sec", "value": val, "unit": "patches/s", "n_gpus": args.gpus, "steps": steps,
+                "warmup": 0, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 samples / f64 optimizer", "data": "synthetic", "config": config,
+                "run": dict(tree_levels=levels, **fountain_quality(fin[:, :3], fin[:, 5])),
+                "cpu_baseline": {"value": val, "unit": "patches/s", "cores": threads, "kind": "reference",
+                                 "sample": "the whole scene through the reference's own CLI (src/main.cpp), its loop time as it logs it"},
+                "e2e": {"value": val, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        _OUT.write(json.dumps(line) + "\n"); _OUT.flush()
+        return
+    import torch
+    import hpmvs_b200 as hp
+    from hpmvs_b200 import gather, pipeline
+    torch.cuda.set_device(0)
+    eng = hp.Engine.from_synth(sc)
+    eng.set_start_mode(True)
+    seeds, valid = hp.seed_patches(eng.options, eng.cameras, sc.points, sc.meas_offsets, sc.meas_cam)
+    seeds = np.ascontiguousarray(seeds[valid])
+    # root cube and start level as Scene::initPatches forms them (Scene.cpp:167-199, DynOctTree::add(e, width), doctree.h:379-394)
+    pre = eng.optimize(seeds)
+    okp = (pre["status"] == 0) & ~(np.linalg.norm(pre["center"][:, :3] - seeds["center"][:, :3], axis=1) > pre["scale"] * 2)
+    origin, width = gather.root_cube(np.ascontiguousarray(pre[okp]))
+    sc3 = np.maximum(pre["scale"][okp], np.float32(width / 1024.0))
+    first_level = int(np.ceil(np.log2(width / (2.0 * sc3.astype(np.float64)))).min())
+    secs, out, stats = [], None, None
+    eng.counters(reset=True)
+    for k in range(steps + 1):                       # the first run warms the engine up (graph + slot creation)
+        t = time.perf_counter()
+        out, stats = pipeline.run_native(eng, seeds, origin=origin, root_width=width, start_level=first_level, final_level=20)
+        if k:
+            secs.append(time.perf_counter() - t)
+        else:
+            eng.counters(reset=True)
+    cnt = eng.counters(reset=True)
+    t_mean = sum(secs) / len(secs)
+    val = len(out) / t_mean
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    alg = (TEX_BYTES * cnt.textures + 2 * REC_BYTES * cnt.patches) / len(secs)
+    line = {"metric": "optimized patches/sec", "value": val, "unit": "patches/s", "n_gpus": 1, "steps": steps, "warmup": 1,
+            "ms_per_step": 1e3 * t_mean, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 samples / f64 optimizer", "data": "synthetic", "config": config,
+            "run": dict(tree_levels=[lv for lv, _, _ in stats.per_level], per_level=stats.per_level, optimize_calls=int(stats.optimized_calls),
+                        optimized_ok=int(stats.optimized_ok), seconds_optimize=stats.seconds_optimize, seconds_accept=stats.seconds_accept,
+                        optimize_calls_per_second=stats.optimized_calls / t_mean,
+                        **fountain_quality(out["center"][:, :3].astype(np.float64), out["normal"][:, 2])),
+            "e2e": {"value": val, "unit": "patches/s", "h2d_bytes_per_step": int(cnt.patches * REC_BYTES / len(secs)),
+                    "d2h_bytes_per_step": int(cnt.patches * REC_BYTES / len(secs)), "ms_per_step": 1e3 * t_mean,
+                    "note": "every batch of the loop crosses the C ABI with host buffers: value == e2e"},
+            "gpu_launches": int(cnt.kernel_launches),
+            "roofline": {"bound": "hbm", "achieved": (alg / stats.seconds_optimize / 1e9) if stats.seconds_optimize else None,
+                         "peak": peak, "unit": "GB/s", "frac": (alg / stats.seconds_optimize / 1e9 / peak) if stats.seconds_optimize else None,
+                         "traffic": None, "kernel": "the fused-path kernels of all batches of one run (see the default workload)",
+                         "note": "algorithmic bytes of one run / time spent inside hpmvs_optimize_batch during that run"},
+            "cpu_baseline": None}
+    _OUT.write(json.dumps(line) + "\n"); _OUT.flush()
+
+
 _OUT = sys.stdout
 
 
@@ -274,6 +385,10 @@ def main():
     args = parse_args()
     global _OUT
     _OUT = _claim_stdout()
+    if args.workload == "fountain11":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_fountain(args)
+        return
     if args.impl == "reference":
         run_reference(args)
         return
