@@ -121,7 +121,8 @@ struct hpmvs_engine {
     // wavefront form of the fused path (patch_kernels_wf.cuh): 0 = persistent kernels, 1 = per-phase kernels in a CUDA-graph WHILE loop,
     // 2 = the same kernels launched round by round from the host (debugging; the call blocks), -1 = 1 for batches >= wf_min_batch else 0
     int wf_mode = 0;
-    int wf_min_batch = 20000;        // synchronous call (one batch at a time): 10 k patches 24.5 ms persistent vs ~35 ms wavefront, 44 k: 88 vs 77 ms
+    int wf_min_batch = 32000;        // synchronous call (one batch at a time; profiles/r2_sync_call_latency_by_batch_size.txt): 24 k patches 44.2 ms
+                                     // persistent vs 46.0 ms wavefront, 40 k: 64.1 vs 59.6 ms, 96 k: 156.6 vs 127.5 ms
     int wf_min_batch_async = 4000;   // asynchronous / device-resident calls (the caller keeps several batches in flight): with 8 in flight the
                                      // wavefront kernels win from ~5 k patches on (5.5 k: 10.1 vs 15.9 ms, 11 k: 16.0 vs 22.4 ms per step)
     int wf_split = 0;                // 1: advance phases A / T / B as three kernels, 0: one kernel with every phase (default: 61.5 vs 71.7 ms per city100 step)
