@@ -104,6 +104,7 @@ struct hpmvs_engine {
     size_t cap_stage = 0;
     int* d_work = nullptr;           // HP_RING work counters: launches on different streams may be in flight together
     cudaEvent_t slot_done[4] = {nullptr, nullptr, nullptr, nullptr};   // slot k is reused only after its previous launch finished
+    cudaStream_t slot_stream[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long launch_seq = 0;
     unsigned long long* d_counters = nullptr;
     unsigned long long launches = 0;
@@ -144,10 +145,12 @@ struct hpmvs_engine {
         WfContext part[HP_WF_PARTS];
         cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
         cudaEvent_t done = nullptr;
+        cudaStream_t last_stream = nullptr;
     } wfb[HP_WF_BATCHES];
     int wf_parts = 1;                // a batch is cut into up to this many sub-batches: their round loops interleave on the GPU
     unsigned long long wf_seq = 0;
     int wf_last = 0;                 // batch context of the most recent wavefront launch
+    unsigned long long opt_calls = 0, last_concurrent_call = 0;   // asynchronous calls seen / the last one that found other streams busy
     unsigned long long wf_overruns = 0;
     std::mutex mu;
 };
@@ -737,6 +740,7 @@ static int launch_wavefront(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, h
     for (int k = 0; k < parts; k++) HP_CUDA(cudaMemcpyAsync(b.part[k].h_ctl, b.part[k].ctl, sizeof(hp::WfCtl), cudaMemcpyDeviceToHost, s));
     HP_CUDA(cudaEventRecord(e->ev1, s));
     HP_CUDA(cudaEventRecord(b.done, s));
+    b.last_stream = s;
     HP_CUDA(cudaGetLastError());
     return 0;
 }
@@ -747,6 +751,21 @@ static int launch_optimize(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, hp
     if (rc) return rc;
     rc = sync_cameras(e);
     if (rc) return rc;
+    if (async_call && e->wf_mode < 0) {
+        // An asynchronous caller that keeps several batches in flight ON DIFFERENT STREAMS gets the throughput-optimal choice (wavefront
+        // kernels from 4 k patches on); one that runs a batch at a time (nothing in flight, or only earlier launches on this very
+        // stream, which are serialised anyway) gets the latency-optimal one (persistent kernel below 32 k patches).
+        bool concurrent = false;
+        for (auto& b : e->wfb) if (b.done && b.last_stream != s && cudaEventQuery(b.done) != cudaSuccess) concurrent = true;
+        for (int i = 0; i < HP_RING; i++)
+            if (e->slot_done[i] && e->slot_stream[i] && e->slot_stream[i] != s && cudaEventQuery(e->slot_done[i]) != cudaSuccess) concurrent = true;
+        (void)cudaGetLastError();
+        // sticky for a while: the first launch after a drained pipeline (start of a timed region, a synchronisation point) belongs to
+        // the same multi-stream caller as the 64 launches before it
+        e->opt_calls++;
+        if (concurrent) e->last_concurrent_call = e->opt_calls;
+        if (!concurrent && (e->last_concurrent_call == 0 || e->opt_calls - e->last_concurrent_call > 64)) async_call = false;
+    }
     if (e->wf_mode > 0 || (e->wf_mode < 0 && n >= (async_call ? e->wf_min_batch_async : e->wf_min_batch))) return launch_wavefront(e, n, d_in, d_out, s);
     // launches on different streams overlap (a CTA of the next launch starts on an SM as soon as the previous launch's CTA
     // there has drained its slots): every launch gets its own work counter from a small ring; a ring slot is reused only after
@@ -801,6 +820,7 @@ static int launch_optimize(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, hp
     }
     HP_CUDA(cudaEventRecord(e->ev1, s));
     HP_CUDA(cudaEventRecord(e->slot_done[slot], s));
+    e->slot_stream[slot] = s;
     e->launches++;
     HP_CUDA(cudaGetLastError());
     return 0;

@@ -16,6 +16,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <cstdio>
 #include <chrono>
 #include <algorithm>
 #include <unordered_map>
@@ -52,6 +53,7 @@ struct Driver {
     double origin[3];
     std::unordered_map<int64_t, int> sub_rank;      // (level, cell key) -> rank, from the sub-tree table
     std::vector<int> sub_levels;
+    bool trace = getenv("HPMVS_PIPELINE_TRACE") != nullptr;     // one stderr line per engine batch (debugging / profiling)
 
     double width(int level) const { return p->root_width / (double)(1 << level); }
     bool exchanging() const { return p->exchange != nullptr && p->shard_count > 1; }
@@ -97,7 +99,9 @@ struct Driver {
         if (r.empty()) return 0;
         const auto t0 = std::chrono::steady_clock::now();
         const int rc = hpmvs_optimize_batch(e, (int)r.size(), r.data(), r.data(), nullptr);
-        st.seconds_optimize += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        st.seconds_optimize += dt;
+        if (trace) fprintf(stderr, "[hpmvs pipeline] optimize batch of %7d patches: %8.2f ms\n", (int)r.size(), 1e3 * dt);
         st.optimize_calls += (int64_t)r.size();
         for (const hpmvs_patch_t& q : r) st.optimized_ok += (q.status == HPMVS_OK);
         return rc;
