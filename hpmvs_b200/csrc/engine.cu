@@ -150,6 +150,7 @@ struct hpmvs_engine {
     int wf_parts = 1;                // a batch is cut into up to this many sub-batches: their round loops interleave on the GPU
     unsigned long long wf_seq = 0;
     int wf_last = 0;                 // batch context of the most recent wavefront launch
+    int wf_sampler_ctas_per_sm = 6;
     unsigned long long opt_calls = 0, last_concurrent_call = 0;   // asynchronous calls seen / the last one that found other streams busy
     unsigned long long wf_overruns = 0;
     std::mutex mu;
@@ -317,6 +318,13 @@ int hpmvs_engine_create(const hpmvs_options_t* opt, int device, hpmvs_engine_t**
     if (const char* wf = getenv("HPMVS_WF")) e->wf_mode = atoi(wf);
     if (const char* ws = getenv("HPMVS_WF_SPLIT")) e->wf_split = atoi(ws);
     if (const char* wm = getenv("HPMVS_WF_MIN_BATCH")) e->wf_min_batch = e->wf_min_batch_async = atoi(wm);
+    {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hp::wf_eval_kernel, hp::WF_SAMPLER_WARPS * 32,
+                                                          sizeof(hp::NccWarp) * hp::WF_SAMPLER_WARPS) == cudaSuccess && occ >= 1)
+            e->wf_sampler_ctas_per_sm = occ > 8 ? 8 : occ;
+        if (const char* sc = getenv("HPMVS_WF_SAMPLER_CTAS")) e->wf_sampler_ctas_per_sm = atoi(sc);
+    }
     e->wf_capacity = e->sm_count * 12 * 32;                                 // one full wave of advance threads (12 warps per SM)
     if (const char* wp = getenv("HPMVS_WF_PARTS")) e->wf_parts = atoi(wp);
     if (e->wf_parts < 1) e->wf_parts = 1;
@@ -590,7 +598,9 @@ struct WfLaunchShape { dim3 grid_s, grid_p, grid_a; size_t smem_s; };
 static WfLaunchShape wf_shape(const hpmvs_engine* e, const hpmvs_engine::WfContext& w) {
     WfLaunchShape sh;
     sh.smem_s = sizeof(hp::NccWarp) * hp::WF_SAMPLER_WARPS;
-    int per_sm = 7 / e->wf_parts;                                      // 7 CTAs x 4 warps x 7 KB per SM, shared by the sub-batches in flight
+    // as many sampler CTAs as are RESIDENT per SM (4 warps x ~9 KB scratch each: 6 per SM): the scoring kernel strides statically over its
+    // list, so a CTA that has to wait for a free slot would start its share only after the others have finished theirs
+    int per_sm = e->wf_sampler_ctas_per_sm / e->wf_parts;
     if (per_sm < 2) per_sm = 2;
     sh.grid_s = dim3((unsigned)(e->sm_count * per_sm));
     sh.grid_p = dim3((unsigned)(e->sm_count * (per_sm > 4 ? 4 : per_sm)));   // post pass: dynamic tickets; most rounds it has nothing to do
