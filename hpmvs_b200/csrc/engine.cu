@@ -693,9 +693,6 @@ static int wf_prepare_part(hpmvs_engine* e, hpmvs_engine::WfContext& w, int n, c
     return 0;
 }
 
-// A batch is cut into up to wf_parts contiguous sub-batches, each with its own round loop (own slots, lists, WHILE node) in ONE graph.
-// Every round of a sub-batch is a chain of latency-bound kernels (ncu: the SMs are > 85 % idle during an advance kernel), so the
-// branches interleave on the GPU: while one sub-batch is in its optimizer phase others sample.
 // Choose an in-flight slot (wavefront batch context / host-buffer staging set): an idle one that already owns its buffers, else a fresh
 // one (buffers + graph are created on first use: tens of milliseconds), else the oldest (the caller's stream then waits for it).  The
 // number of slots that ever get created is thus the number of launches the caller really keeps in flight.
@@ -712,6 +709,9 @@ static int pick_slot(Slot* a, int n, unsigned long long& rr) {
 }
 extern "C" {
 
+// One launch = one CUDA graph: fill kernel -> WHILE loop over the rounds (wf_build_graph).  HPMVS_WF_PARTS > 1 cuts the batch into
+// contiguous sub-batches with their own loops as parallel branches of that graph (measured: no gain over one loop, default 1;
+// what pays is keeping whole launches in flight on different streams, each on its own WfBatch).
 static int launch_wavefront(hpmvs_engine* e, int n, const hpmvs_patch_t* d_in, hpmvs_patch_t* d_out, cudaStream_t s) {
     const double* d_start = e->next_start;
     e->next_start = nullptr;
